@@ -1,0 +1,429 @@
+// Element-wise, mixing, DEEP and FRI-fold kernels (sm_100a).
+//
+// Stand-ins for the risc0-zkp `Hal` methods eltwise_{add,copy,zeroize}_elem, eltwise_sum_extelem, fri_fold,
+// mix_poly_coeffs, batch_evaluate_any, gather_sample, prefix_products, zk_shift, batch_expand,
+// batch_bit_reverse (risc0-sys kernels/zkp/cuda/*.cu in the CudaHal) and for the
+// host-side `poly_divide` step of Prover::finalize (core/poly.rs; App. C.13), which is kept on the device here.
+// All are HBM-bound streaming kernels except the DEEP evaluation (4 modmul per coefficient).
+#include "common.cuh"
+
+namespace zkb {
+
+struct Fp4Arg { uint32_t w[4]; };
+__host__ __device__ inline Fp4 arg4(const Fp4Arg& a) { return Fp4::load(a.w); }
+inline Fp4Arg to_arg(const Fp4& x) { Fp4Arg a; x.store(a.w); return a; }
+inline Fp4Arg to_arg(const uint32_t* w) { Fp4Arg a; memcpy(a.w, w, 16); return a; }
+
+constexpr int EW_BLOCK = 256;
+
+// ---- trivial element-wise ----------------------------------------------------------------------------
+__global__ void k_add(uint32_t* __restrict__ o, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = add_mod(a[i], b[i]);
+}
+__global__ void k_zeroize(uint32_t* __restrict__ x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && x[i] == INVALID) x[i] = 0;
+}
+__global__ void k_fill(uint32_t* __restrict__ x, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+__global__ void k_gather(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t idx, size_t size, size_t stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < size) dst[i] = src[idx + i * stride];
+}
+__global__ void k_expand(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, size_t total_out, int expand_bits) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total_out) out[i] = in[i >> expand_bits];     // columns are contiguous, so this holds across the batch
+}
+// in-place bit reversal of each column
+__global__ void k_bit_reverse(uint32_t* __restrict__ io, int po2, size_t count) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)1 << po2;
+  if (g >= n * count) return;
+  uint32_t i = (uint32_t)(g & (n - 1));
+  uint32_t r = bit_rev32(i, po2);
+  if (i < r) {
+    uint32_t* col = io + (g - i);
+    uint32_t a = col[i], b = col[r];
+    col[i] = b; col[r] = a;
+  }
+}
+// io[c][i] *= 3^bitrev(i)
+__global__ void k_zk_shift(uint32_t* __restrict__ io, int po2, size_t count) {
+  size_t n = (size_t)1 << po2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp s = pow(Fp::from(3), bit_rev32((uint32_t)i, po2));
+  for (size_t c = 0; c < count; ++c) io[c * n + i] = mont_mul(io[c * n + i], s.v);
+}
+
+// ---- eltwise_sum_extelem / fri_fold ----------------------------------------------------------------------
+__global__ void k_sum_extelem(uint32_t* __restrict__ out, const uint4* __restrict__ in, size_t count, size_t to_add) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  for (size_t k = 0; k < to_add; ++k) {
+    uint4 v = in[k * count + idx];
+    t0 = add_mod(t0, v.x); t1 = add_mod(t1, v.y); t2 = add_mod(t2, v.z); t3 = add_mod(t3, v.w);
+  }
+  out[idx] = t0; out[count + idx] = t1; out[2 * count + idx] = t2; out[3 * count + idx] = t3;
+}
+__global__ void k_fri_fold(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, Fp4Arg mix_arg, size_t m) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m) return;
+  Fp4 mix = arg4(mix_arg), tot, cur = Fp4::one();
+#pragma unroll 4
+  for (uint32_t i = 0; i < 16; ++i) {
+    size_t r = (size_t)bit_rev32(i, 4) * m + idx;
+    Fp4 v = Fp4::raw(in[r], in[16 * m + r], in[32 * m + r], in[48 * m + r]);
+    tot += cur * v;
+    cur *= mix;
+  }
+  out[idx] = tot.c[0].v; out[m + idx] = tot.c[1].v; out[2 * m + idx] = tot.c[2].v; out[3 * m + idx] = tot.c[3].v;
+}
+
+// ---- mix_poly_coeffs --------------------------------------------------------------------------------------
+// pw[i] = start * mix^i
+__global__ void k_mix_powers(uint4* __restrict__ pw, Fp4Arg start, Fp4Arg mix, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp4 r = arg4(start) * pow(arg4(mix), i);
+  pw[i] = st4(r);
+}
+// grid.y = combo id; each thread owns out[combo][idx] and sweeps the columns that map to this combo.
+constexpr int MIX_CHUNK = 256;
+__global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict__ out, const uint4* __restrict__ pw, const uint32_t* __restrict__ in,
+                                                               const uint32_t* __restrict__ combos, uint32_t input_size, size_t count) {
+  __shared__ uint4 s_pw[MIX_CHUNK];
+  __shared__ uint32_t s_combo[MIX_CHUNK];
+  const uint32_t combo = blockIdx.y;
+  size_t idx = (size_t)blockIdx.x * EW_BLOCK + threadIdx.x;
+  bool live = idx < count;
+  Fp4 acc;
+  bool any = false;
+  for (uint32_t base = 0; base < input_size; base += MIX_CHUNK) {
+    uint32_t chunk = min((uint32_t)MIX_CHUNK, input_size - base);
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < chunk; t += EW_BLOCK) { s_pw[t] = pw[base + t]; s_combo[t] = combos[base + t]; }
+    __syncthreads();
+    if (!live) continue;
+    for (uint32_t t = 0; t < chunk; ++t) {
+      if (s_combo[t] != combo) continue;      // uniform across the block
+      uint4 p = s_pw[t];
+      Fp v = Fp::raw(__ldg(in + (size_t)(base + t) * count + idx));
+      acc += ld4(p) * v;
+      any = true;
+    }
+  }
+  if (live && any) {
+    uint4* o = out + (size_t)combo * count + idx;
+    uint4 cur = *o;
+    Fp4 r = ld4(cur) + acc;
+    *o = st4(r);
+  }
+}
+
+// ---- batch_evaluate_any (DEEP) -------------------------------------------------------------------------
+// Slab kernel: block (slab, j) evaluates sum_{i in slab} coeffs[which[j]][i] * x^i.  Each warp sweeps a
+// contiguous run of its slab with coalesced loads; lane l accumulates sum_m c[32m + l] * (x^32)^m with 4 modmul
+// per coefficient, and the x^l / x^(warp base) / x^(slab base) factors are applied once at the end.
+constexpr int EVAL_THREADS = 256, EVAL_WARPS = EVAL_THREADS / 32, EVAL_STEPS = 64;
+constexpr size_t EVAL_SLAB = (size_t)EVAL_THREADS * EVAL_STEPS;     // 16384 coefficients
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__ partial, const uint32_t* __restrict__ coeffs, size_t n,
+                                                              const uint32_t* __restrict__ which, const uint4* __restrict__ xs, uint32_t n_slabs) {
+  __shared__ uint4 s_x32[EVAL_STEPS];
+  __shared__ uint4 s_red[EVAL_WARPS];
+  const uint32_t slab = blockIdx.x, j = blockIdx.y;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 xv = xs[j];
+  const Fp4 x = ld4(xv);
+  if (threadIdx.x < EVAL_STEPS) {
+    Fp4 x32 = x;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x32 *= x32;
+    Fp4 p = pow(x32, threadIdx.x);
+    s_x32[threadIdx.x] = st4(p);
+  }
+  __syncthreads();
+  const uint32_t* col = coeffs + (size_t)which[j] * n;
+  size_t warp_base = (size_t)slab * EVAL_SLAB + (size_t)warp * (32 * EVAL_STEPS);
+  Fp4 acc;
+#pragma unroll 4
+  for (int m = 0; m < EVAL_STEPS; ++m) {
+    size_t i = warp_base + (size_t)m * 32 + lane;
+    uint32_t c = i < n ? __ldg(col + i) : 0u;
+    uint4 p = s_x32[m];
+    acc += ld4(p) * Fp(c);
+  }
+  acc *= pow(x, lane);
+  // warp reduction
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    Fp4 o = Fp4::raw(__shfl_down_sync(0xffffffffu, acc.c[0].v, off), __shfl_down_sync(0xffffffffu, acc.c[1].v, off),
+                     __shfl_down_sync(0xffffffffu, acc.c[2].v, off), __shfl_down_sync(0xffffffffu, acc.c[3].v, off));
+    acc += o;
+  }
+  if (lane == 0) {
+    acc *= pow(x, (uint64_t)warp_base);
+    s_red[warp] = st4(acc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Fp4 t;
+    for (int w = 0; w < EVAL_WARPS; ++w) { uint4 v = s_red[w]; t += ld4(v); }
+    partial[(size_t)j * n_slabs + slab] = st4(t);
+  }
+}
+__global__ void k_eval_reduce(uint4* __restrict__ out, const uint4* __restrict__ partial, uint32_t n_slabs, uint32_t n_eval) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_eval) return;
+  Fp4 t;
+  for (uint32_t s = 0; s < n_slabs; ++s) { uint4 v = partial[(size_t)j * n_slabs + s]; t += ld4(v); }
+  out[j] = st4(t);
+}
+
+// ---- poly_divide (synthetic division by x - z), Fp4 coefficients -----------------------------------------
+// Recurrence: next = z*cur + p[i]; p[i] = cur  (i descending).  Parallelised by chunks of DIV_CHUNK: pass 1 computes
+// each chunk's Horner total, the totals are divided recursively by (X - z^DIV_CHUNK) -- which yields exactly every
+// chunk's carry-in and the global remainder -- and pass 2 replays each chunk from its carry.
+constexpr int DIV_CHUNK = 64;
+__global__ void k_div_totals(uint4* __restrict__ totals, const uint4* __restrict__ p, size_t n, Fp4Arg z_arg) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = c * DIV_CHUNK;
+  if (lo >= n) return;
+  size_t hi = min(lo + (size_t)DIV_CHUNK, n);
+  Fp4 z = arg4(z_arg), acc;
+  for (size_t i = hi; i-- > lo;) { uint4 v = p[i]; acc = acc * z + ld4(v); }
+  totals[c] = st4(acc);
+}
+__global__ void k_div_apply(uint4* __restrict__ p, const uint4* __restrict__ carries, size_t n, Fp4Arg z_arg) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = c * DIV_CHUNK;
+  if (lo >= n) return;
+  size_t hi = min(lo + (size_t)DIV_CHUNK, n);
+  Fp4 z = arg4(z_arg);
+  uint4 cv = carries[c];
+  Fp4 cur = ld4(cv);
+  for (size_t i = hi; i-- > lo;) {
+    uint4 v = p[i];
+    Fp4 next = z * cur + ld4(v);
+    p[i] = st4(cur);
+    cur = next;
+  }
+}
+__global__ void k_div_serial(uint4* __restrict__ p, size_t n, Fp4Arg z_arg, uint4* __restrict__ rem) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fp4 z = arg4(z_arg), cur;
+  for (size_t i = n; i-- > 0;) {
+    uint4 v = p[i];
+    Fp4 next = z * cur + ld4(v);
+    p[i] = st4(cur);
+    cur = next;
+  }
+  *rem = st4(cur);
+}
+
+// ---- prefix_products (Fp4 inclusive product scan) -----------------------------------------------------
+constexpr int PP_CHUNK = 64;
+__global__ void k_pp_totals(uint4* __restrict__ totals, const uint4* __restrict__ io, size_t n) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = c * PP_CHUNK;
+  if (lo >= n) return;
+  size_t hi = min(lo + (size_t)PP_CHUNK, n);
+  Fp4 acc = Fp4::one();
+  for (size_t i = lo; i < hi; ++i) { uint4 v = io[i]; acc *= ld4(v); }
+  totals[c] = st4(acc);
+}
+__global__ void k_pp_apply(uint4* __restrict__ io, const uint4* __restrict__ scanned_totals, size_t n) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = c * PP_CHUNK;
+  if (lo >= n) return;
+  size_t hi = min(lo + (size_t)PP_CHUNK, n);
+  Fp4 acc = Fp4::one();
+  if (c > 0) { uint4 v = scanned_totals[c - 1]; acc = ld4(v); }
+  for (size_t i = lo; i < hi; ++i) {
+    uint4 v = io[i];
+    acc *= ld4(v);
+    io[i] = st4(acc);
+  }
+}
+__global__ void k_pp_serial(uint4* __restrict__ io, size_t n) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fp4 acc = Fp4::one();
+  for (size_t i = 0; i < n; ++i) {
+    uint4 v = io[i];
+    acc *= ld4(v);
+    io[i] = st4(acc);
+  }
+}
+
+// ---- host-side launchers (shared with prover.cu) --------------------------------------------------------
+void eltwise_add(zkb_ctx* ctx, uint32_t* o, const uint32_t* a, const uint32_t* b, size_t n) {
+  if (!n) return;
+  k_add<<<grid_for(n, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(o, a, b, n); launched(ctx);
+}
+void eltwise_zeroize(zkb_ctx* ctx, uint32_t* x, size_t n) {
+  if (!n) return;
+  k_zeroize<<<grid_for(n, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(x, n); launched(ctx);
+}
+void fill_u32(zkb_ctx* ctx, uint32_t* x, size_t n, uint32_t v) {
+  if (!n) return;
+  k_fill<<<grid_for(n, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(x, n, v); launched(ctx);
+}
+void gather_sample(zkb_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
+  if (!size) return;
+  k_gather<<<grid_for(size, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(dst, src, idx, size, stride); launched(ctx);
+}
+void batch_expand(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, int in_po2, int expand_bits) {
+  size_t total = (count << in_po2) << expand_bits;
+  if (!total) return;
+  k_expand<<<grid_for(total, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(out, in, total, expand_bits); launched(ctx);
+}
+void batch_bit_reverse(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
+  size_t total = count << po2;
+  if (!total || po2 == 0) return;
+  k_bit_reverse<<<grid_for(total, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(io, po2, count); launched(ctx);
+}
+void zk_shift(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
+  size_t n = (size_t)1 << po2;
+  if (!count) return;
+  k_zk_shift<<<grid_for(n, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(io, po2, count); launched(ctx);
+}
+void eltwise_sum_extelem(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add) {
+  if (!count) return;
+  k_sum_extelem<<<grid_for(count, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(out, (const uint4*)in, count, to_add); launched(ctx);
+}
+void fri_fold(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t m) {
+  if (!m) return;
+  k_fri_fold<<<grid_for(m, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(out, in, to_arg(mix), m); launched(ctx);
+}
+void mix_poly_coeffs(zkb_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in, const uint32_t* d_combos,
+                     size_t input_size, size_t count, uint32_t n_combo_slots) {
+  if (!input_size || !count) return;
+  uint4* pw = (uint4*)scratch(ctx, input_size * 16);
+  k_mix_powers<<<grid_for(input_size, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(pw, to_arg(mix_start), to_arg(mix), (uint32_t)input_size); launched(ctx);
+  dim3 grid(grid_for(count, EW_BLOCK), n_combo_slots);
+  k_mix_poly_coeffs<<<grid, EW_BLOCK, 0, ctx->stream>>>((uint4*)out, pw, in, d_combos, (uint32_t)input_size, count); launched(ctx);
+}
+void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval) {
+  if (!n_eval) return;
+  size_t n = (size_t)1 << po2;
+  uint32_t n_slabs = (uint32_t)((n + EVAL_SLAB - 1) / EVAL_SLAB);
+  uint4* partial = (uint4*)scratch(ctx, n_eval * n_slabs * 16);
+  for (size_t j0 = 0; j0 < n_eval; j0 += 32768) {      // grid.y limit
+    uint32_t nj = (uint32_t)std::min<size_t>(32768, n_eval - j0);
+    dim3 grid(n_slabs, nj);
+    k_eval_slabs<<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, (const uint4*)d_xs + j0, n_slabs); launched(ctx);
+  }
+  k_eval_reduce<<<grid_for(n_eval, 128), 128, 0, ctx->stream>>>((uint4*)d_out, partial, n_slabs, (uint32_t)n_eval); launched(ctx);
+}
+// d_work: caller-provided device scratch of >= 2 * ceil(n / DIV_CHUNK) Fp4 (or nullptr to use a temporary)
+void poly_divide(zkb_ctx* ctx, uint32_t* d_poly, size_t n, const Fp4& z, uint32_t* d_rem) {
+  if (n <= 4 * DIV_CHUNK) {
+    k_div_serial<<<1, 32, 0, ctx->stream>>>((uint4*)d_poly, n, to_arg(z), (uint4*)d_rem); launched(ctx);
+    return;
+  }
+  size_t chunks = (n + DIV_CHUNK - 1) / DIV_CHUNK;
+  uint4* totals = nullptr;
+  ZKB_CUDA(cudaMallocAsync((void**)&totals, chunks * 16, ctx->stream));
+  k_div_totals<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>(totals, (const uint4*)d_poly, n, to_arg(z)); launched(ctx);
+  poly_divide(ctx, (uint32_t*)totals, chunks, pow(z, DIV_CHUNK), d_rem);
+  k_div_apply<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>((uint4*)d_poly, totals, n, to_arg(z)); launched(ctx);
+  ZKB_CUDA(cudaFreeAsync(totals, ctx->stream));
+}
+void prefix_products(zkb_ctx* ctx, uint32_t* d_io, size_t n) {
+  if (n <= 4 * PP_CHUNK) {
+    if (n) { k_pp_serial<<<1, 32, 0, ctx->stream>>>((uint4*)d_io, n); launched(ctx); }
+    return;
+  }
+  size_t chunks = (n + PP_CHUNK - 1) / PP_CHUNK;
+  uint4* totals = nullptr;
+  ZKB_CUDA(cudaMallocAsync((void**)&totals, chunks * 16, ctx->stream));
+  k_pp_totals<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>(totals, (const uint4*)d_io, n); launched(ctx);
+  prefix_products(ctx, (uint32_t*)totals, chunks);
+  k_pp_apply<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>((uint4*)d_io, totals, n); launched(ctx);
+  ZKB_CUDA(cudaFreeAsync(totals, ctx->stream));
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+static inline void check_po2(int po2) { ZKB_REQUIRE(po2 >= 0 && po2 <= MAX_PO2, "po2 out of range [0, 26]"); }
+
+extern "C" {
+
+zkb_err zkb_fill_u32(zkb_ctx* ctx, void* d_ptr, size_t n, uint32_t value) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE(d_ptr || !n, "null buffer"); fill_u32(ctx, (uint32_t*)d_ptr, n, value); ZKB_API_END
+}
+zkb_err zkb_eltwise_add_elem(zkb_ctx* ctx, void* d_out, const void* d_a, const void* d_b, size_t n) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_out && d_a && d_b) || !n, "null buffer"); eltwise_add(ctx, (uint32_t*)d_out, (const uint32_t*)d_a, (const uint32_t*)d_b, n); ZKB_API_END
+}
+zkb_err zkb_eltwise_copy_elem(zkb_ctx* ctx, void* d_out, const void* d_in, size_t n) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_out && d_in) || !n, "null buffer");
+  if (n) ZKB_CUDA(cudaMemcpyAsync(d_out, d_in, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  ZKB_API_END
+}
+zkb_err zkb_eltwise_zeroize_elem(zkb_ctx* ctx, void* d_io, size_t n) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE(d_io || !n, "null buffer"); eltwise_zeroize(ctx, (uint32_t*)d_io, n); ZKB_API_END
+}
+zkb_err zkb_gather_sample(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t idx, size_t size, size_t stride) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_dst && d_src) || !size, "null buffer"); gather_sample(ctx, (uint32_t*)d_dst, (const uint32_t*)d_src, idx, size, stride); ZKB_API_END
+}
+zkb_err zkb_prefix_products(zkb_ctx* ctx, void* d_io_fp4, size_t n) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_io_fp4 && aligned16(d_io_fp4)) || !n, "null or misaligned buffer"); prefix_products(ctx, (uint32_t*)d_io_fp4, n); ZKB_API_END
+}
+zkb_err zkb_zk_shift(zkb_ctx* ctx, void* d_io, size_t count, int po2) {
+  ZKB_API_BEGIN use(ctx); check_po2(po2); ZKB_REQUIRE(d_io || !count, "null buffer"); zk_shift(ctx, (uint32_t*)d_io, count, po2); ZKB_API_END
+}
+zkb_err zkb_batch_expand(zkb_ctx* ctx, void* d_out, const void* d_in, size_t count, int in_po2, int expand_bits) {
+  ZKB_API_BEGIN use(ctx); check_po2(in_po2); ZKB_REQUIRE(expand_bits >= 0 && in_po2 + expand_bits <= MAX_PO2, "expand_bits out of range");
+  ZKB_REQUIRE((d_out && d_in) || !count, "null buffer");
+  batch_expand(ctx, (uint32_t*)d_out, (const uint32_t*)d_in, count, in_po2, expand_bits);
+  ZKB_API_END
+}
+zkb_err zkb_batch_bit_reverse(zkb_ctx* ctx, void* d_io, size_t count, int po2) {
+  ZKB_API_BEGIN use(ctx); check_po2(po2); ZKB_REQUIRE(d_io || !count, "null buffer"); batch_bit_reverse(ctx, (uint32_t*)d_io, count, po2); ZKB_API_END
+}
+zkb_err zkb_eltwise_sum_extelem(zkb_ctx* ctx, void* d_out, const void* d_in, size_t count, size_t to_add) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_out && d_in && aligned16(d_in)) || !count, "null or misaligned buffer");
+  eltwise_sum_extelem(ctx, (uint32_t*)d_out, (const uint32_t*)d_in, count, to_add);
+  ZKB_API_END
+}
+zkb_err zkb_fri_fold(zkb_ctx* ctx, void* d_out, const void* d_in, const uint32_t* h_mix, size_t out_count) {
+  ZKB_API_BEGIN use(ctx); ZKB_REQUIRE(((d_out && d_in) || !out_count) && h_mix, "null buffer");
+  fri_fold(ctx, (uint32_t*)d_out, (const uint32_t*)d_in, Fp4::load(h_mix), out_count);
+  ZKB_API_END
+}
+zkb_err zkb_mix_poly_coeffs(zkb_ctx* ctx, void* d_out, const uint32_t* h_mix_start, const uint32_t* h_mix, const void* d_in, const void* d_combos,
+                            size_t input_size, size_t count) {
+  ZKB_API_BEGIN use(ctx);
+  ZKB_REQUIRE(d_out && d_in && d_combos && h_mix_start && h_mix, "null buffer");
+  ZKB_REQUIRE(aligned16(d_out), "out must be 16-byte aligned");
+  // combo slots present: read the ids back once (tiny) to size the grid
+  std::vector<uint32_t> ids(input_size);
+  ZKB_CUDA(cudaMemcpyAsync(ids.data(), d_combos, input_size * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint32_t slots = 0;
+  for (uint32_t v : ids) slots = std::max(slots, v + 1);
+  ZKB_REQUIRE(slots <= 65535, "combo id too large");
+  mix_poly_coeffs(ctx, (uint32_t*)d_out, Fp4::load(h_mix_start), Fp4::load(h_mix), (const uint32_t*)d_in, (const uint32_t*)d_combos, input_size, count, slots);
+  ZKB_API_END
+}
+zkb_err zkb_batch_evaluate_any(zkb_ctx* ctx, const void* d_coeffs, size_t poly_count, int po2, const void* d_which, const void* d_xs, void* d_out, size_t n_eval) {
+  ZKB_API_BEGIN use(ctx); check_po2(po2); (void)poly_count;
+  ZKB_REQUIRE((d_coeffs && d_which && d_xs && d_out) || !n_eval, "null buffer");
+  ZKB_REQUIRE(aligned16(d_xs) && aligned16(d_out), "xs/out must be 16-byte aligned");
+  batch_evaluate_any(ctx, (const uint32_t*)d_coeffs, po2, (const uint32_t*)d_which, (const uint32_t*)d_xs, (uint32_t*)d_out, n_eval);
+  ZKB_API_END
+}
+zkb_err zkb_poly_divide(zkb_ctx* ctx, void* d_poly, size_t n, const uint32_t* h_z, void* d_rem) {
+  ZKB_API_BEGIN use(ctx);
+  ZKB_REQUIRE(d_poly && h_z && d_rem && aligned16(d_poly) && aligned16(d_rem), "null or misaligned buffer");
+  poly_divide(ctx, (uint32_t*)d_poly, n, Fp4::load(h_z), (uint32_t*)d_rem);
+  ZKB_API_END
+}
+
+}  // extern "C"
