@@ -1,0 +1,78 @@
+"""GPU parity of the full segment prover: seal words and Merkle/FRI roots from libzkb200 must equal the CPU oracle's
+(the stand-in for "identical Merkle roots, FRI commitments and receipt" -- SURVEY.md 4.2, 8d config 2)."""
+import numpy as np
+import pytest
+
+from zktls_b200 import circuit, synth
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(accum_cols=4, code_cols=3, data_cols=6, mix_size=5, out_size=4)
+MID = dict(accum_cols=7, code_cols=5, data_cols=33, mix_size=20, out_size=32)
+
+
+@pytest.fixture(scope="module")
+def hal():
+    from zktls_b200.hal import B200Hal
+    h = B200Hal(0)
+    yield h
+    h.close()
+
+
+def run_both(hal, oracle, shape, po2, seed, valid):
+    from zktls_b200.prover import SegmentProver
+    blob = circuit.syn_circuit(**shape).blob()
+    gp = SegmentProver(hal, blob); op = oracle.Prover(blob)
+    if valid:
+        io, code, data = synth.trace_b_code_data(shape, po2, seed)
+        code_m, data_m = synth.to_mont(code), synth.to_mont(data)
+        mix_g = gp.begin(po2, io, code_m, data_m); mix_o = op.begin(po2, io, code_m, data_m)
+        assert np.array_equal(mix_g, mix_o)
+        accum_m = synth.to_mont(synth.trace_b_accum(shape, po2, seed, code, data, io, mix_g))
+        seal_g = gp.finish(accum_m); seal_o = op.finish(accum_m)
+    else:
+        io, code_m, data_m, accum_m = synth.trace_a(shape, po2, seed)
+        seal_g = gp.prove(po2, io, code_m, data_m, accum_m)
+        op.begin(po2, io, code_m, data_m); seal_o = op.finish(accum_m)
+    roots_g, roots_o = gp.roots(), op.roots()
+    gp.close()
+    return seal_g, seal_o, roots_g, roots_o
+
+
+@pytest.mark.parametrize("shape,po2,valid", [(SMALL, 8, True), (SMALL, 10, True), (SMALL, 10, False), (MID, 12, True), (SMALL, 13, False), (MID, 14, False)])
+def test_seal_matches_oracle(hal, oracle, shape, po2, valid):
+    seal_g, seal_o, roots_g, roots_o = run_both(hal, oracle, shape, po2, seed=11 + po2, valid=valid)
+    assert np.array_equal(roots_g, roots_o), "Merkle / FRI roots differ"
+    assert seal_g.size == seal_o.size
+    diff = np.nonzero(seal_g != seal_o)[0]
+    assert diff.size == 0, f"first differing seal word at {diff[:5]} of {seal_g.size}"
+
+
+def test_syn280_seal_matches_oracle(hal, oracle):
+    """The benchmark circuit (SYN-280) at a size the oracle proves in seconds."""
+    seal_g, seal_o, roots_g, roots_o = run_both(hal, oracle, circuit.SYN280, 11, seed=5, valid=False)
+    assert np.array_equal(roots_g, roots_o) and np.array_equal(seal_g, seal_o)
+
+
+def test_device_resident_traces_give_the_same_seal(hal, oracle):
+    from zktls_b200.prover import SegmentProver
+    po2 = 10
+    blob = circuit.syn_circuit(**SMALL).blob()
+    io, code_m, data_m, accum_m = synth.trace_a(SMALL, po2, 21)
+    p1 = SegmentProver(hal, blob); s1 = p1.prove(po2, io, code_m, data_m, accum_m); p1.close()
+    p2 = SegmentProver(hal, blob)
+    s2 = p2.prove(po2, io, hal.copy_from_elem(code_m), hal.copy_from_elem(data_m), hal.copy_from_elem(accum_m)); p2.close()
+    assert np.array_equal(s1, s2)
+
+
+@pytest.mark.parametrize("po2", [6, 9])
+def test_eval_check_matches_oracle(hal, oracle, po2):
+    shape = MID
+    blob = circuit.syn_circuit(**shape).blob()
+    rng = np.random.default_rng(po2)
+    dom = 4 << po2
+    accum, code, data = (oracle.random_fp(rng, shape[k] * dom) for k in ("accum_cols", "code_cols", "data_cols"))
+    mix, out, pm = oracle.random_fp(rng, shape["mix_size"]), oracle.random_fp(rng, shape["out_size"]), oracle.random_fp(rng, 4)
+    chk = hal.alloc_elem(4 * dom)
+    hal.eval_check(chk, blob, hal.copy_from_elem(accum), hal.copy_from_elem(code), hal.copy_from_elem(data), mix, out, pm, po2)
+    assert np.array_equal(chk.to_numpy(), oracle.eval_check(blob, accum, code, data, mix, out, pm, po2))
