@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 proving backend on BASELINE.json's metric: segments proven/sec (2^20 cycles).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" proves ONE synthetic 2^20-cycle segment of the SYN-280 circuit (BASELINE.json configs[1]):
+iNTT + zk-shift, x4 coset LDE, Poseidon2 row hashing + Merkle commit for the code/data/accum/check groups,
+eval_check, DEEP evaluation + mixing + on-device division, three FRI rounds and the 50 queries -- the whole
+`prove_segment` transcript, ending with the seal on the host.
+
+  value  = segments/s with the three trace groups already resident in HBM when the timed region starts
+  e2e    = the same through the reference-facing C-ABI call with HOST (pinned) trace buffers: the 1.17 GB host->device
+           copy and the seal read-back are inside the timed region
+  roofline = live CUDA-event timing of the dominant kernel (Poseidon2 hash_rows over the data group's 224 x 2^22 LDE
+           matrix) against the measured HBM peak; `int32` adds the modmul rate, the bound that actually applies
+  cpu_baseline = the CPU oracle (C++ restatement of CpuHal, OpenMP) on a bounded sample on this box's host cores
+
+Segments are independent (continuations), so N GPUs prove N segments per step with no data-path collective
+("scaling": "weak"); the only collectives are the timing barrier / max-reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "segments proven/sec (2^20 cycles)"
+UNIT = "segments/s"
+PO2 = 20
+P = 2013265921
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the busy half (samples taken while the GPU was idle between steps would drag it down)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+def cpu_baseline(sample_po2, threads=None):
+    """The oracle prover (restated CpuHal) on a SYN-280 segment of 2^sample_po2 cycles, all host threads."""
+    from zktls_b200 import circuit, synth
+    from oracle import oracle as O
+    if threads:
+        O.lib().orc_set_num_threads(int(threads))
+    cores = O.lib().orc_num_threads()
+    blob = circuit.syn_circuit(**circuit.SYN280).blob()
+    io, code, data, accum = synth.trace_a(circuit.SYN280, sample_po2, 0xB200)
+    t0 = time.time()
+    pr = O.Prover(blob)
+    pr.begin(sample_po2, io, code, data)
+    pr.finish(accum)
+    dt = time.time() - t0
+    scale = 1 << (PO2 - sample_po2)
+    return dt, cores, dt * scale
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  The Rust crates cannot be built here (no
+    cargo, source un-vendored), so this is the oracle port (oracle/, C++/OpenMP restatement of CpuHal)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_po2 = args.cpu_sample_po2 or 16
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(min(sample_po2, 12))
+    times = []
+    cores = 0
+    for _ in range(args.steps):
+        dt, cores, full = cpu_baseline(sample_po2)
+        times.append(full)
+    ms = 1000.0 * sum(times) / len(times)
+    value = 1000.0 / ms
+    sample = f"SYN-280 segment of 2^{sample_po2} cycles per step, time x{1 << (PO2 - sample_po2)} (work is linear in rows up to the log factor of the NTTs)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "syn280-segment-po2-20: one synthetic 2^20-cycle rv32im-shaped segment (BASELINE.json configs[1]): iNTT+zk-shift, x4 LDE, "
+                        "Poseidon2 Merkle commit of code/data/accum/check, eval_check, DEEP + mix + divide, 3 FRI rounds, 50 queries; seal on host",
+            "po2": PO2, "columns": {"accum": 40, "code": 16, "data": 224, "check": 16}, "trace": "A (uniform field elements, seeded)",
+            "l2": "inputs (1.17 GB trace, 4.7 GB LDE) exceed the 126 MB L2, no flush needed", "parallelism": "segment-parallel, one process per GPU, no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
+    ap.add_argument("--cpu-sample-po2", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from zktls_b200 import circuit
+    from zktls_b200.hal import B200Hal
+    from zktls_b200.prover import SegmentProver
+
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    po2 = args.po2
+    n = 1 << po2
+    shape = circuit.SYN280
+    blob = circuit.syn_circuit(**shape).blob()
+    hal = B200Hal(local_rank)
+    prover = SegmentProver(hal, blob)
+
+    # synthetic trace, generated on the device (uniform field elements), seeded per rank
+    g = torch.Generator(device=dev); g.manual_seed(0xB2000000 + rank)
+    def rand_fp(count):
+        return torch.randint(0, P, (count,), device=dev, dtype=torch.int64, generator=g).to(torch.int32)   # < 2^31: same bits as u32
+    d_code, d_data, d_accum = rand_fp(shape["code_cols"] * n), rand_fp(shape["data_cols"] * n), rand_fp(shape["accum_cols"] * n)
+    io = np.random.default_rng(rank).integers(0, P, size=shape["out_size"], dtype=np.uint32)
+    from zktls_b200.hal import Buffer
+    as_buf = lambda t: Buffer(hal, t.data_ptr(), t.numel(), 1, owner=t)
+    b_code, b_data, b_accum = as_buf(d_code), as_buf(d_data), as_buf(d_accum)
+    # pinned host copies for the end-to-end arm
+    h_code, h_data, h_accum = (t.cpu().pin_memory() for t in (d_code, d_data, d_accum))
+    h_np = [t.numpy().view(np.uint32) for t in (h_code, h_data, h_accum)]
+    trace_bytes = sum(t.numel() * 4 for t in (d_code, d_data, d_accum))
+    torch.cuda.synchronize()
+
+    def step_device():
+        return prover.prove(po2, io, b_code, b_data, b_accum)
+
+    def step_host():
+        return prover.prove(po2, io, h_np[0], h_np[1], h_np[2])
+
+    # ---- device-resident arm -----------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        seal = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = hal.kernel_launches()
+    hal.timer_start(); t0 = time.time()
+    for _ in range(args.steps):
+        seal = step_device()
+    ms_dev = hal.timer_stop()
+    barrier()
+    wall = time.time() - t0
+    launches = hal.kernel_launches() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * args.steps / (ms_total / 1000.0)
+
+    # ---- end-to-end arm: host buffers through the C-ABI prove call ------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        seal_h = step_host()
+    barrier()
+    hal.timer_start()
+    for _ in range(args.steps):
+        seal_h = step_host()
+    ms_e2e = hal.timer_stop()
+    barrier()
+    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / (float(t.item()) / 1000.0)
+    assert np.array_equal(seal, seal_h), "device-resident and host-buffer paths disagree"
+
+    # ---- roofline of the dominant kernel (hash_rows over the data group's LDE matrix), live CUDA events -----------------
+    roof = None
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        rows, cols = 4 * n, shape["data_cols"]
+        mat = hal.alloc_elem(rows * cols)           # contents irrelevant for timing; zero-initialised
+        dig = hal.alloc_digest(rows)
+        for _ in range(3):
+            hal.hash_rows(dig, mat)
+        reps = 5
+        hal.timer_start()
+        for _ in range(reps):
+            hal.hash_rows(dig, mat)
+        ms = hal.timer_stop() / reps
+        alg_bytes = 4 * rows * cols + 32 * rows
+        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        perms = rows * ((cols + 15) // 16)
+        roof = {"bound": "hbm", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind, "ms_per_launch": ms,
+                "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation",
+                          "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3)}}
+        del mat, dig
+        # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT and x4 LDE over 64 columns of 2^20
+        ntt_cols = 64
+        buf = hal.alloc_elem(ntt_cols * n); big = hal.alloc_elem(ntt_cols * 4 * n)
+        for _ in range(2):
+            hal.batch_interpolate_ntt_zk_shift(buf, ntt_cols); hal.batch_expand_into_evaluate_ntt(big, buf, ntt_cols, 2)
+        hal.timer_start()
+        for _ in range(reps):
+            hal.batch_interpolate_ntt_zk_shift(buf, ntt_cols)
+        ms_i = hal.timer_stop() / reps
+        hal.timer_start()
+        for _ in range(reps):
+            hal.batch_expand_into_evaluate_ntt(big, buf, ntt_cols, 2)
+        ms_l = hal.timer_stop() / reps
+        roof["ntt"] = {"intt_zk_shift": {"cols": ntt_cols, "po2": po2, "ms": ms_i, "GBps": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9, "frac": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                       "lde_x4": {"cols": ntt_cols, "po2": po2, "ms": ms_l, "GBps": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9, "frac": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+        del buf, big
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_po2 = args.cpu_sample_po2 or 17
+        dt, cores, full = cpu_baseline(sample_po2)
+        cpu = {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle prover (C++/OpenMP restatement of CpuHal) on one SYN-280 segment of 2^{sample_po2} cycles: {dt:.2f} s, x{1 << (PO2 - sample_po2)} for 2^20"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
+                "config": workload_config(), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4)},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
+        if po2 != PO2:
+            line["config"]["workload"] = f"DEBUG po2={po2} (not the benchmark config)"
+        print(json.dumps(line), flush=True)
+    prover.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
