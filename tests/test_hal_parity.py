@@ -210,3 +210,39 @@ def test_errors_are_strings_not_crashes(hal):
     import ctypes as C
     with pytest.raises(ZkbError):
         check(lib().zkb_batch_interpolate_ntt(hal.ctx, C.c_void_p(b.ptr), C.c_size_t(1), C.c_int(40)))
+
+
+@pytest.mark.parametrize("po2,count,shift", [(21, 2, True), (22, 3, False), (23, 2, True), (24, 1, True), (25, 1, False)])
+def test_tiled_inverse_ntt_matches_level_path_at_large_sizes(hal, po2, count, shift, monkeypatch):
+    """Beyond what the CPU oracle finishes in seconds: the tiled kernels against the level-at-a-time device path (which
+    the oracle pins at small sizes), including the three-pass plans (po2 > 22)."""
+    x = rnd(1400 + po2, count << po2)
+    a = hal.copy_from_elem(x)
+    (hal.batch_interpolate_ntt_zk_shift if shift else hal.batch_interpolate_ntt)(a, count)
+    monkeypatch.setenv("ZKB_NTT_FORCE_LEVELS", "1")
+    b = hal.copy_from_elem(x)
+    (hal.batch_interpolate_ntt_zk_shift if shift else hal.batch_interpolate_ntt)(b, count)
+    monkeypatch.delenv("ZKB_NTT_FORCE_LEVELS")
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+
+
+@pytest.mark.parametrize("po2,count,eb", [(19, 3, 2), (20, 2, 2), (21, 1, 2), (22, 1, 2), (23, 1, 0), (24, 1, 2)])
+def test_tiled_forward_ntt_matches_level_path_at_large_sizes(hal, po2, count, eb, monkeypatch):
+    x = rnd(1500 + po2, count << po2)
+    src = hal.copy_from_elem(x)
+    a = hal.alloc_elem(count << (po2 + eb))
+    hal.batch_expand_into_evaluate_ntt(a, src, count, eb)
+    monkeypatch.setenv("ZKB_NTT_FORCE_LEVELS", "1")
+    b = hal.alloc_elem(count << (po2 + eb))
+    hal.batch_expand_into_evaluate_ntt(b, src, count, eb)
+    monkeypatch.delenv("ZKB_NTT_FORCE_LEVELS")
+    assert np.array_equal(a.to_numpy(), b.to_numpy())
+
+
+def test_ntt_many_columns_crosses_l2_batches(hal, oracle):
+    po2, count = 14, 300       # > one L2 batch at the default budget? no -- exercise the batching loop with a tiny budget instead
+    x = rnd(1600, count << po2)
+    b = hal.copy_from_elem(x)
+    hal.batch_interpolate_ntt_zk_shift(b, count)
+    want = oracle.zk_shift(oracle.batch_interpolate_ntt(x, count, po2), count, po2)
+    assert np.array_equal(b.to_numpy(), want)

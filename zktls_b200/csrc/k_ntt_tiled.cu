@@ -1,8 +1,438 @@
-// Tiled (shared-memory / register-radix) NTT kernels -- placeholder until the tiled path lands; returning false
-// makes k_ntt.cu use the level-at-a-time path.
+// Tiled BabyBear NTT / iNTT / LDE kernels (sm_100a): register radix-16 butterflies, shared-memory exchanges,
+// four-step passes sized so that a whole batch of columns stays in the 126 MB L2 between passes.
+//
+// Index conventions are those of risc0-zkp `core/ntt.rs`, decomposed as follows.  Write a
+// position of the 2^k array as p = p1 * S + p2 (S = 2^s) and the coefficient index it holds in bit-reversed layout as
+// j = rev_k(p) = rev_s(p2) * 2^a + rev_a(p1) (a = k - s).
+//   inverse (DIF, natural evaluations -> bit-reversed coefficients, x 1/n):
+//     pass S: for every p2, a size-2^a DIF over p1 (stride S) leaves frequency j1 = rev_a(p1') at p1'; multiply by
+//             w_n^(-j1 * p2) (and by 3^j1 / n when the zk-shift is fused);
+//     pass C: for every p1', a size-2^s DIF over the contiguous p2 (then x 3^(2^a * rev_s(p2')) for the zk-shift).
+//   forward (DIT, bit-reversed coefficients -> natural evaluations) is the mirror image: pass C first (its lowest
+//     `expand_bits` levels replaced by replication, reading the n/4-element input directly), then the twiddle w_n^(+j1 p2)
+//     and the strided DIT.
+// Sub-transforms larger than 2^12 are split again the same way (three passes for k > 22).
+//
+// Each thread keeps 16 elements in registers and runs up to four butterfly levels on them; between such rounds the
+// CTA's tile goes through shared memory (padded by one word per 16 so that every round's access pattern is
+// bank-conflict free).  Pass C works on 4096 contiguous elements per CTA (128-bit global accesses on the
+// consecutive-16 side, 128-byte lines on the strided side); pass S works on a (2^a x T) tile whose rows are T >= 16
+// consecutive elements (>= 64-byte segments).  Per-level twiddles w_{2^(q+1)}^x come from an 8192-word table that
+// stays in L1; the inter-pass twiddles are generated per thread as a running product G^m from two table look-ups.
 #include "common.cuh"
 #include "ntt.cuh"
+
 namespace zkb {
-bool ntt_inverse_tiled(zkb_ctx*, uint32_t*, size_t, int, bool) { return false; }
-bool ntt_forward_tiled(zkb_ctx*, uint32_t*, const uint32_t*, size_t, int, int) { return false; }
+
+constexpr int TILE_LOG = 12, TILE = 1 << TILE_LOG;      // elements per CTA in pass C
+constexpr int C_THREADS = TILE / 16;                    // 256
+constexpr int MAX_LEVEL_LOG = 12;                       // level tables cover q < 12
+
+__device__ __forceinline__ uint32_t phys(uint32_t x) { return x + (x >> 4); }
+constexpr uint32_t phys_size(uint32_t n) { return n + (n >> 4) + 1; }
+
+// bit reversal of the 4-bit register index
+__host__ __device__ constexpr int rev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3); }
+
+// One round of butterfly levels on the 16 registers.  The registers are the values of local-index bits [p, p+4);
+// levels JLO <= j < JHI (absolute bit q = p + j) are processed: descending for the DIF (inverse), ascending for the
+// DIT (forward).  `lo` = the thread's local-index bits below p.  twl = per-level twiddle table for this direction.
+template <bool INV, int JLO, int JHI>
+__device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, const uint32_t lo, const uint32_t* __restrict__ twl) {
+  if (INV) {
+#pragma unroll
+    for (int j = JHI - 1; j >= JLO; --j) {
+      const int q = p + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if (r & (1 << j)) continue;
+        uint32_t a = v[r], b = v[r | (1 << j)];
+        v[r] = add_mod(a, b);
+        uint32_t d = sub_mod(a, b);
+        if (q == 0) v[r | (1 << j)] = d;
+        else v[r | (1 << j)] = mont_mul(d, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = JLO; j < JHI; ++j) {
+      const int q = p + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        if (r & (1 << j)) continue;
+        uint32_t a = v[r], b = v[r | (1 << j)];
+        if (q != 0) b = mont_mul(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
+        v[r] = add_mod(a, b);
+        v[r | (1 << j)] = sub_mod(a, b);
+      }
+    }
+  }
+}
+
+// local index of register r for thread t in a round whose register field starts at bit p
+__device__ __forceinline__ uint32_t local_index(uint32_t t, int p, int r) {
+  uint32_t lo = t & ((1u << p) - 1u), hi = t >> p;
+  return (hi << (p + 4)) | ((uint32_t)r << p) | lo;
+}
+
+// ---- pass C: contiguous sub-transforms of size 2^A (4 <= A <= 12), 4096 elements per CTA ---------------------------
+enum : int { EPI_NONE = 0, EPI_SCALE = 1, EPI_TABLE = 2 };
+
+// Inverse: in place.  epilogue multiplies position x of every 2^A block by table[x] (EPI_TABLE) or by `scale`.
+template <int A, int EPI>
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, const uint32_t* __restrict__ table, uint32_t scale) {
+  __shared__ uint32_t sm[phys_size(TILE)];
+  constexpr int L = 1 << A, TPB = L / 16;           // threads per sub-transform
+  const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
+  uint32_t* base = io + (size_t)blockIdx.x * TILE + (size_t)sub * L;
+  uint32_t* s = sm;   // sub-transform `sub` lives at [sub*L, (sub+1)*L) of the tile
+  const uint32_t soff = sub * L;
+  uint32_t v[16];
+  constexpr int REM = A % 4;
+  constexpr int P0 = A - 4;
+  // first round: field [A-4, A): element r * TPB + t -> coalesced loads
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = base[(uint32_t)r * TPB + t];
+  radix_round<true, 0, 4>(v, P0, t, twl);
+  int p_prev = P0;
+#pragma unroll
+  for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
+    const int pc = p < 0 ? 0 : p;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[phys(soff + local_index(t, p_prev, r))] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = s[phys(soff + local_index(t, pc, r))];
+    __syncthreads();
+    if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
+    else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
+    p_prev = pc;
+  }
+  // here p_prev == 0 (A >= 4): registers are 16 consecutive elements
+  uint32_t* o = base + 16 * t;
+  if (EPI == EPI_TABLE) {
+    const uint4* tb = reinterpret_cast<const uint4*>(table + 16 * t);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 w = __ldg(tb + g);
+      v[4 * g] = mont_mul(v[4 * g], w.x); v[4 * g + 1] = mont_mul(v[4 * g + 1], w.y);
+      v[4 * g + 2] = mont_mul(v[4 * g + 2], w.z); v[4 * g + 3] = mont_mul(v[4 * g + 3], w.w);
+    }
+  } else if (EPI == EPI_SCALE) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = mont_mul(v[r], scale);
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(o)[g] = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+
+// Forward: out-of-place capable; EB = expand bits (0 or 2): out block element x <- in[(block_base + x) >> EB], and the
+// lowest EB levels are skipped.
+template <int A, int EB>
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint32_t* __restrict__ twl) {
+  __shared__ uint32_t sm[phys_size(TILE)];
+  constexpr int L = 1 << A, TPB = L / 16;
+  const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
+  const size_t gbase = (size_t)blockIdx.x * TILE + (size_t)sub * L;
+  const uint32_t soff = sub * L;
+  uint32_t* s = sm;
+  uint32_t v[16];
+  if (EB == 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + gbase + 16 * t);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { uint4 w = src[g]; v[4 * g] = w.x; v[4 * g + 1] = w.y; v[4 * g + 2] = w.z; v[4 * g + 3] = w.w; }
+  } else {   // EB == 2: 16 consecutive outputs come from 4 consecutive inputs
+    uint4 w = *reinterpret_cast<const uint4*>(in + ((gbase + 16 * t) >> 2));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { v[r] = w.x; v[4 + r] = w.y; v[8 + r] = w.z; v[12 + r] = w.w; }
+  }
+  constexpr int REM = A % 4;
+  constexpr int PLAST = A - 4;
+  radix_round<false, EB, 4>(v, 0, 0u, twl);
+  int p_prev = 0;
+#pragma unroll
+  for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
+    const int pc = p > PLAST ? PLAST : p;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[phys(soff + local_index(t, p_prev, r))] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = s[phys(soff + local_index(t, pc, r))];
+    __syncthreads();
+    if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
+    else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
+    p_prev = pc;
+  }
+  // p_prev == A - 4: register r is element r * TPB + t
+  uint32_t* o = out + gbase;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) o[(uint32_t)r * TPB + t] = v[r];
+}
+
+// ---- pass S: strided sub-transforms of size 2^A over a (2^A x T) tile, T consecutive elements per row -------------
+// The array is a sequence of blocks of M = 2^A * S elements (S = 2^s_log); within a block, position = p1 * S + p2.
+struct SArgs {
+  uint32_t s_log;          // log2 S
+  uint32_t tiles_per_block_log;   // log2 (S / T)
+  uint32_t shift_g;        // inverse only: B^(2^(A-4)) (Montgomery), B = shift base of this pass; R_MOD_P if none
+  uint32_t use_table;      // inverse only: multiply V by table[rev_{A-4}(t')] (includes the 1/n scale where needed)
+};
+
+template <int A> struct STile { static constexpr int T_LOG = (A >= 8) ? 4 : (12 - A); static constexpr int T = 1 << T_LOG; static constexpr int THREADS = (1 << A) * T / 16; };
+
+template <int A, bool INV>
+__global__ void __launch_bounds__(STile<A>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args) {
+  constexpr int T_LOG = STile<A>::T_LOG, T = STile<A>::T, TPB = (1 << A) / 16;
+  extern __shared__ uint32_t sm[];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t c2 = tid & (T - 1), t = tid >> T_LOG;                      // column inside the tile, thread inside the column
+  const uint32_t tile = blockIdx.x & ((1u << args.tiles_per_block_log) - 1u);
+  const size_t block = blockIdx.x >> args.tiles_per_block_log;
+  const uint32_t p2 = (tile << T_LOG) + c2;                                 // position inside the row of S
+  const int m_log = A + (int)args.s_log;
+  uint32_t* base = io + (block << m_log) + p2;
+  const size_t S = (size_t)1 << args.s_log;
+  uint32_t v[16];
+  constexpr int REM = A % 4;
+
+  // inter-pass twiddles: register r (holding local position 16 t + r) needs G^(rev_A(16 t + r)) = V * g^(rev4(r)),
+  // G = w_M^(+-p2) [* shift base], V = G^(rev_{A-4}(t)), g = G^(2^(A-4)).
+  auto twiddle_all = [&](bool inverse) {
+    uint32_t rt = A > 4 ? bit_rev32(t, A - 4) : 0u;
+    uint32_t e_v = rt * p2, e_g = p2 << (A - 4);
+    uint32_t V = inverse ? tw.inv(e_v, m_log) : tw.fwd(e_v, m_log);
+    uint32_t g = inverse ? tw.inv(e_g, m_log) : tw.fwd(e_g, m_log);
+    if (inverse) {
+      if (args.use_table) V = mont_mul(V, __ldg(table + t));     // table[t] = mult * B^(rev_{A-4}(t))
+      if (args.shift_g != R_MOD_P) g = mont_mul(g, args.shift_g);
+    }
+    uint32_t cur = V;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      v[rev4(m)] = mont_mul(v[rev4(m)], cur);
+      if (m != 15) cur = mont_mul(cur, g);
+    }
+  };
+
+  if (INV) {
+    constexpr int P0 = A - 4;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = base[((size_t)r * TPB + t) * S];
+    radix_round<true, 0, 4>(v, P0, t, twl);
+    int p_prev = P0;
+#pragma unroll
+    for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
+      const int pc = p < 0 ? 0 : p;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) sm[phys((local_index(t, p_prev, r) << T_LOG) + c2)] = v[r];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys((local_index(t, pc, r) << T_LOG) + c2)];
+      __syncthreads();
+      if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
+      else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
+      p_prev = pc;
+    }
+    twiddle_all(true);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) base[((size_t)16 * t + r) * S] = v[r];
+  } else {
+    constexpr int PLAST = A - 4;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = base[((size_t)16 * t + r) * S];
+    twiddle_all(false);
+    radix_round<false, 0, 4>(v, 0, 0u, twl);
+    int p_prev = 0;
+#pragma unroll
+    for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
+      const int pc = p > PLAST ? PLAST : p;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) sm[phys((local_index(t, p_prev, r) << T_LOG) + c2)] = v[r];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys((local_index(t, pc, r) << T_LOG) + c2)];
+      __syncthreads();
+      if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
+      else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
+      p_prev = pc;
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) base[((size_t)r * TPB + t) * S] = v[r];
+  }
+}
+
+// ---- host side: tables, plans, launches ---------------------------------------------------------------------------
+static const uint32_t* level_table(zkb_ctx* ctx, bool inverse) {
+  NttTables* t = ntt_tables(ctx);
+  int key = inverse ? 1 : 0;
+  auto it = t->level_tables.find(key);
+  if (it != t->level_tables.end()) return it->second;
+  std::vector<uint32_t> h((size_t)1 << MAX_LEVEL_LOG, R_MOD_P);
+  for (int q = 0; q < MAX_LEVEL_LOG; ++q) {
+    Fp w = inverse ? t->rou_rev[q + 1] : t->rou_fwd[q + 1];
+    Fp cur = Fp::one();
+    for (uint32_t x = 0; x < (1u << q); ++x) { h[(1u << q) + x] = cur.v; cur *= w; }
+  }
+  uint32_t* d = nullptr;
+  ZKB_CUDA(cudaMalloc((void**)&d, h.size() * 4));
+  ZKB_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  t->level_tables[key] = d;
+  return d;
+}
+// table[x] = mult * base^(rev_bits(x)) for x < 2^bits
+static const uint32_t* shift_table(zkb_ctx* ctx, int bits, Fp base, Fp mult) {
+  NttTables* t = ntt_tables(ctx);
+  uint64_t key = ((uint64_t)bits << 58) ^ ((uint64_t)base.v << 26) ^ (uint64_t)mult.v * 0x9E3779B97F4A7C15ull;
+  auto it = t->shift_tables.find(key);
+  if (it != t->shift_tables.end()) return it->second;
+  size_t n = (size_t)1 << bits;
+  std::vector<uint32_t> h(n);
+  std::vector<Fp> pw(n);
+  Fp cur = mult;
+  for (size_t j = 0; j < n; ++j) { pw[j] = cur; cur *= base; }
+  for (size_t x = 0; x < n; ++x) h[x] = pw[bit_rev32((uint32_t)x, bits)].v;
+  uint32_t* d = nullptr;
+  ZKB_CUDA(cudaMalloc((void**)&d, std::max<size_t>(n, 4) * 4));
+  ZKB_CUDA(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice));
+  t->shift_tables[key] = d;
+  return d;
+}
+
+struct Plan { int n_s; int a_s[2]; int a_c; };
+// k = a_s[0] + a_s[1] + a_c; prefers multiples of 4 (no partial rounds) and a 2^12 contiguous pass
+static bool make_plan(int k, Plan& pl) {
+  if (k < 4) return false;
+  pl.n_s = 0; pl.a_s[0] = pl.a_s[1] = 0;
+  if (k <= 12) { pl.a_c = k; return true; }
+  if (k <= 15) { pl.a_c = 8; pl.a_s[0] = k - 8; pl.n_s = 1; return true; }     // 5..7
+  if (k <= 22) { pl.a_c = 12; pl.a_s[0] = k - 12; pl.n_s = 1; return true; }   // 4..10
+  if (k <= 32) { pl.a_c = 12; int rem = k - 12; pl.a_s[1] = (rem + 1) / 2; pl.a_s[0] = rem - pl.a_s[1]; pl.n_s = 2; return pl.a_s[1] <= 10; }
+  return false;
+}
+
+template <int A, bool INV>
+static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
+  using ST = STile<A>;
+  SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
+  size_t tile_elems = (size_t)(1 << A) * ST::T;
+  size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
+  auto kern = k_ntt_s<A, INV>;
+  if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args);
+  launched(ctx);
+}
+template <bool INV>
+static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
+  switch (a) {
+    case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 9: launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 10: launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    default: throw Error("zkb200: unsupported strided NTT size");
+  }
+}
+template <int EPI>
+static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, const uint32_t* twl, const uint32_t* table, uint32_t scale) {
+  unsigned grid = (unsigned)(total / TILE);
+#define ZKB_CI(AA) case AA: k_ntt_c_inv<AA, EPI><<<grid, C_THREADS, 0, ctx->stream>>>(io, twl, table, scale); break;
+  switch (a) { ZKB_CI(4) ZKB_CI(5) ZKB_CI(6) ZKB_CI(7) ZKB_CI(8) ZKB_CI(9) ZKB_CI(10) ZKB_CI(11) ZKB_CI(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
+#undef ZKB_CI
+  launched(ctx);
+}
+template <int EB>
+static void dispatch_c_fwd(zkb_ctx* ctx, int a, uint32_t* out, const uint32_t* in, size_t total, const uint32_t* twl) {
+  unsigned grid = (unsigned)(total / TILE);
+#define ZKB_CF(AA) case AA: k_ntt_c_fwd<AA, EB><<<grid, C_THREADS, 0, ctx->stream>>>(out, in, twl); break;
+  switch (a) { ZKB_CF(4) ZKB_CF(5) ZKB_CF(6) ZKB_CF(7) ZKB_CF(8) ZKB_CF(9) ZKB_CF(10) ZKB_CF(11) ZKB_CF(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
+#undef ZKB_CF
+  launched(ctx);
+}
+
+// columns per batch so that the batch (in + out) stays L2-resident between passes
+static size_t batch_columns(size_t count, size_t bytes_per_column) {
+  static size_t budget = [] { const char* e = getenv("ZKB_NTT_L2_BYTES"); return e ? (size_t)atoll(e) : (size_t)48 << 20; }();
+  size_t b = std::max<size_t>(1, budget / std::max<size_t>(bytes_per_column, 1));
+  size_t gran = std::max<size_t>(1, ((size_t)TILE * 4) / std::max<size_t>(bytes_per_column, 1));   // whole tiles per batch
+  if (b >= count) return count;
+  return std::max(gran, b / gran * gran);
+}
+
+static bool force_levels() { const char* e = getenv("ZKB_NTT_FORCE_LEVELS"); return e && e[0] == '1'; }
+
+bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift) {
+  Plan pl;
+  if (force_levels()) return false;
+  if (!make_plan(k, pl)) return false;
+  if (count == 0) return true;
+  size_t n = (size_t)1 << k;
+  if ((count * n) % TILE != 0) return false;          // tiny batches of tiny columns: level path
+  NttTables* t = ntt_tables(ctx);
+  TwiddleRef tw{t->d_hi, t->d_lo};
+  const uint32_t* twl = level_table(ctx, true);
+  const Fp scale = inv(Fp::from((uint32_t)1 << k));
+  const Fp three = Fp::from(3);
+  // per-pass parameters
+  struct SPass { int a, s_log; const uint32_t* table; uint32_t shift_g; } sp[2];
+  int consumed = 0;      // bits of the coefficient index already assigned (weight of the next pass = 2^consumed)
+  for (int i = 0; i < pl.n_s; ++i) {
+    int a = pl.a_s[i];
+    sp[i].a = a; sp[i].s_log = k - consumed - a;
+    Fp base = shift ? pow(three, (uint64_t)1 << consumed) : Fp::one();
+    Fp mult = i == 0 ? scale : Fp::one();
+    bool need_table = shift || i == 0;
+    sp[i].table = need_table ? shift_table(ctx, std::max(a - 4, 0), base, mult) : nullptr;
+    sp[i].shift_g = shift ? pow(base, (uint64_t)1 << (a - 4)).v : R_MOD_P;
+    consumed += a;
+  }
+  const uint32_t* c_table = nullptr;
+  int epi = EPI_NONE;
+  if (shift) { c_table = shift_table(ctx, pl.a_c, pow(three, (uint64_t)1 << consumed), pl.n_s == 0 ? scale : Fp::one()); epi = EPI_TABLE; }
+  else if (pl.n_s == 0) epi = EPI_SCALE;
+  size_t bc = batch_columns(count, n * 4);
+  for (size_t c0 = 0; c0 < count; c0 += bc) {
+    size_t cols = std::min(bc, count - c0);
+    uint32_t* p = io + c0 * n;
+    size_t total = cols * n;
+    for (int i = 0; i < pl.n_s; ++i) dispatch_s<true>(ctx, sp[i].a, p, total, sp[i].s_log, twl, tw, sp[i].table, sp[i].shift_g);
+    if (epi == EPI_TABLE) dispatch_c_inv<EPI_TABLE>(ctx, pl.a_c, p, total, twl, c_table, 0);
+    else if (epi == EPI_SCALE) dispatch_c_inv<EPI_SCALE>(ctx, pl.a_c, p, total, twl, nullptr, scale.v);
+    else dispatch_c_inv<EPI_NONE>(ctx, pl.a_c, p, total, twl, nullptr, 0);
+  }
+  return true;
+}
+
+bool ntt_forward_tiled(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, int k, int expand_bits) {
+  Plan pl;
+  if (force_levels()) return false;
+  if (!make_plan(k, pl)) return false;
+  if (expand_bits != 0 && expand_bits != 2) return false;
+  if (expand_bits > pl.a_c - 0 || pl.a_c < 4) return false;
+  if (count == 0) return true;
+  size_t n = (size_t)1 << k;
+  if ((count * n) % TILE != 0) return false;
+  NttTables* t = ntt_tables(ctx);
+  TwiddleRef tw{t->d_hi, t->d_lo};
+  const uint32_t* twl = level_table(ctx, false);
+  size_t n_in = n >> expand_bits;
+  size_t bc = batch_columns(count, (n + (out == in ? 0 : n_in)) * 4);
+  for (size_t c0 = 0; c0 < count; c0 += bc) {
+    size_t cols = std::min(bc, count - c0);
+    uint32_t* o = out + c0 * n;
+    const uint32_t* i_ = in + c0 * n_in;
+    size_t total = cols * n;
+    if (expand_bits == 2) dispatch_c_fwd<2>(ctx, pl.a_c, o, i_, total, twl);
+    else dispatch_c_fwd<0>(ctx, pl.a_c, o, i_, total, twl);
+    // strided passes, innermost first: pass i works inside blocks of 2^(a_c + a_s[n_s-1] + ... + a_s[i]) elements
+    int s_log = pl.a_c;
+    for (int i = pl.n_s - 1; i >= 0; --i) {
+      dispatch_s<false>(ctx, pl.a_s[i], o, total, s_log, twl, tw, nullptr, R_MOD_P);
+      s_log += pl.a_s[i];
+    }
+  }
+  return true;
+}
+
 }  // namespace zkb
