@@ -45,15 +45,16 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples nvidia-smi clocks / throttle reasons for one GPU.  Started before the warm-up so that nvidia-smi is already
+    streaming when the timed region begins; stop(t0, t1) keeps only the samples whose host time falls inside [t0, t1]."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -62,9 +63,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,19 +75,20 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.05:
+                continue
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+                sm.append(float(f[0])); smax = float(f[1]); power.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[4:8]):
+            for name, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median over the busy half (samples taken while the GPU was idle between steps would drag it down)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
                 "power_w_max": max(power) if power else None}
 
@@ -144,7 +146,7 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
@@ -205,19 +207,20 @@ def main():
         return prover.prove(po2, io, h_np[0], h_np[1], h_np[2])
 
     # ---- device-resident arm -----------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup):
         seal = step_device()
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
     l0 = hal.kernel_launches()
     hal.timer_start(); t0 = time.time()
     for _ in range(args.steps):
         seal = step_device()
     ms_dev = hal.timer_stop()
     barrier()
-    wall = time.time() - t0
+    t1 = time.time()
+    wall = t1 - t0
     launches = hal.kernel_launches() - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t1)
     t = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -119,6 +119,13 @@ zkb_err zkb_eval_check(zkb_ctx* ctx, void* d_check, const uint32_t* h_circuit, s
                        const void* d_code, const void* d_data, const uint32_t* h_mix_g, const uint32_t* h_out_g,
                        const uint32_t* h_poly_mix, int po2);
 
+/* The specialised (NVRTC-compiled) form of eval_check for a circuit: its generated CUDA source (host-only; writes up to
+ * cap bytes NUL-terminated, full length to *needed), and an ahead-of-time compile into the on-disk cubin cache
+ * (ZKB_CACHE_DIR, default /tmp/zkb200-cache) -- the counterpart of the reference compiling its generated poly_fp at
+ * crate build time. */
+zkb_err zkb_eval_check_source(const uint32_t* h_circuit, size_t circuit_words, char* out, size_t cap, size_t* needed);
+zkb_err zkb_eval_check_precompile(const uint32_t* h_circuit, size_t circuit_words);
+
 /* ---- Prover: risc0-zkp prove::Prover + the circuit's prove_segment driver ------------------ */
 zkb_err zkb_prover_new(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_words, zkb_prover** out);
 zkb_err zkb_prover_free(zkb_prover* p);

@@ -18,4 +18,14 @@ elif a.op == "intt":
 elif a.op == "lde":
     b = hal.alloc_elem(a.cols * n); o = hal.alloc_elem(a.cols * 4 * n)
     for _ in range(a.reps): hal.batch_expand_into_evaluate_ntt(o, b, a.cols, 2)
+elif a.op == "eval_check":
+    import os
+    from zktls_b200 import circuit
+    shape = circuit.SYN280; blob = circuit.syn_circuit(**shape).blob(); dom = 4 * n
+    acc = hal.alloc_elem(shape["accum_cols"] * dom); code = hal.alloc_elem(shape["code_cols"] * dom); data = hal.alloc_elem(shape["data_cols"] * dom)
+    chk = hal.alloc_elem(4 * dom); mixg = np.arange(shape["mix_size"], dtype=np.uint32); outg = np.arange(shape["out_size"], dtype=np.uint32); pm = np.array([5, 6, 7, 8], np.uint32)
+    hal.eval_check(chk, blob, acc, code, data, mixg, outg, pm, a.po2); hal.sync()
+    hal.timer_start()
+    for _ in range(a.reps): hal.eval_check(chk, blob, acc, code, data, mixg, outg, pm, a.po2)
+    print("eval_check mode", os.environ.get("ZKB_EVAL_CHECK", "jit"), "minblocks", os.environ.get("ZKB_EC_MINBLOCKS", "4"), "ms/launch", hal.timer_stop() / a.reps)
 hal.timer_start(); hal.sync(); print(a.op, "done, launches", hal.kernel_launches())

@@ -51,7 +51,7 @@ def build(force=False, verbose=False, ptxas_v=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(SO):
-        cmd = [NVCC, "-shared", "-o", SO] + objs + ARCH + ["-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-lcudart"]
+        cmd = [NVCC, "-shared", "-o", SO] + objs + ARCH + ["-ccbin", HOST_CXX, "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -50,6 +50,7 @@ struct zkb_ctx {
   size_t scratch_bytes = 0;
   void* staging = nullptr;                // pinned host staging for small parameter uploads
   size_t staging_bytes = 0;
+  void* jit = nullptr;                    // EvalJitCache* (k_eval_jit.cu): per-circuit NVRTC-compiled eval_check kernels
 };
 
 namespace zkb {
@@ -75,5 +76,6 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 inline unsigned grid_for(size_t work, unsigned block) { return (unsigned)((work + block - 1) / block); }
 
 void ntt_tables_free(zkb_ctx* ctx);   // k_ntt.cu
+void eval_jit_free(zkb_ctx* ctx);     // k_eval_jit.cu
 
 }  // namespace zkb

@@ -43,6 +43,7 @@ zkb_err zkb_destroy(zkb_ctx* ctx) {
   use(ctx);
   cudaStreamSynchronize(ctx->stream);
   ntt_tables_free(ctx);
+  eval_jit_free(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->staging) cudaFreeHost(ctx->staging);
   cudaEventDestroy(ctx->ev0);

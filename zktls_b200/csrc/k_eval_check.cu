@@ -169,9 +169,25 @@ __global__ void __launch_bounds__(EC_BLOCK) k_eval_check(uint32_t* __restrict__ 
   check[c] = tot.c[0].v; check[domain + c] = tot.c[1].v; check[2 * domain + c] = tot.c[2].v; check[3 * domain + c] = tot.c[3].v;
 }
 
+bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint32_t* const d_groups[3], const uint32_t* mix_g, const uint32_t* out_g,
+                    const Fp4& poly_mix, int po2, std::string& why);   // k_eval_jit.cu
+
+// ZKB_EVAL_CHECK = jit (default: NVRTC-specialised kernel, interpreter if NVRTC is unavailable) | vm (interpreter) |
+// jit-only (fail instead of falling back; used by the tests to make sure the JIT path is the one exercised)
 void eval_check(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint32_t* const d_groups[3], const uint32_t* mix_g, const uint32_t* out_g,
                 const Fp4& poly_mix, int po2) {
   ZKB_REQUIRE(po2 >= 0 && po2 + 2 <= MAX_PO2, "eval_check: po2 out of range");
+  {
+    const char* mode = getenv("ZKB_EVAL_CHECK");
+    const bool vm_only = mode && !strcmp(mode, "vm"), jit_only = mode && !strcmp(mode, "jit-only");
+    if (!vm_only) {
+      std::string why;
+      if (eval_check_jit(ctx, d_check, c, d_groups, mix_g, out_g, poly_mix, po2, why)) return;
+      if (jit_only) throw Error("zkb200: eval_check JIT unavailable: " + why);
+      static bool warned = false;
+      if (!warned) { warned = true; fprintf(stderr, "zkb200: eval_check JIT unavailable (%s); using the device interpreter\n", why.c_str()); }
+    }
+  }
   const size_t n = (size_t)1 << po2, domain = n * INV_RATE;
   ZKB_REQUIRE(domain % EC_BLOCK == 0 || domain < EC_BLOCK, "eval_check: domain too small");
   EvalProgram prog = lower(c, mix_g, out_g);
@@ -210,6 +226,27 @@ void eval_check(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint
 }  // namespace zkb
 
 using namespace zkb;
+
+namespace zkb { std::string eval_jit_source(const CircuitDef& c); bool eval_jit_compile_only(const CircuitDef& c, std::string& why); }
+
+// Generated CUDA source of the specialised eval_check kernel (host-only; no device needed).  Writes up to `cap` bytes
+// (NUL-terminated) and the full length (without NUL) to *needed.
+extern "C" zkb_err zkb_eval_check_source(const uint32_t* h_circuit, size_t circuit_words, char* out, size_t cap, size_t* needed) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(h_circuit && needed, "null argument");
+  std::string src = eval_jit_source(CircuitDef::parse(h_circuit, circuit_words));
+  *needed = src.size();
+  if (out && cap) { size_t m = std::min(cap - 1, src.size()); memcpy(out, src.data(), m); out[m] = 0; }
+  ZKB_API_END
+}
+// Compiles that source for sm_100a with NVRTC (host-only) and stores the cubin in the on-disk cache.
+extern "C" zkb_err zkb_eval_check_precompile(const uint32_t* h_circuit, size_t circuit_words) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(h_circuit, "null argument");
+  std::string why;
+  if (!eval_jit_compile_only(CircuitDef::parse(h_circuit, circuit_words), why)) throw Error("zkb200: eval_check precompile failed: " + why);
+  ZKB_API_END
+}
 
 extern "C" zkb_err zkb_eval_check(zkb_ctx* ctx, void* d_check, const uint32_t* h_circuit, size_t circuit_words, const void* d_accum, const void* d_code,
                                   const void* d_data, const uint32_t* h_mix_g, const uint32_t* h_out_g, const uint32_t* h_poly_mix, int po2) {

@@ -1,0 +1,324 @@
+// eval_check, specialised per circuit: the PolyExtStep program is turned into straight-line CUDA C++ and compiled for
+// sm_100a with NVRTC the first time a circuit is seen.
+//
+// The reference gets its `poly_fp` the same way, only ahead of time: risc0-circuit-rv32im-sys compiles a generated
+// C++/CUDA function of ~10^5 lines with nvcc at crate build time (un-vendored; call site
+// /root/reference/crates/guest-prover-r0/src/prover.rs:90).  Here the constraint system arrives as data (circuit.hpp), so
+// the specialisation happens at `zkb_prover_new` / first `zkb_eval_check`:
+//   * every Fp temporary and every mix accumulator is an SSA value in registers (the interpreter in k_eval_check.cu
+//     spends ~65 instructions of decode / shared-memory traffic per PolyExtStep; the compiled form spends 1-5);
+//   * taps are read straight from the column-major LDE matrices, one coalesced 128-byte line per warp and tap;
+//   * per-proof values (globals, powers of poly_mix, the four (3x)^n - 1 inverses) are kernel DATA, so one cubin serves
+//     every segment of the circuit; cubins are cached in memory per ctx and on disk (ZKB_CACHE_DIR, default
+//     /tmp/zkb200-cache) keyed by a hash of the generated source.
+// libnvrtc / libcuda are dlopen'ed, not linked: when they are absent the caller falls back to the device interpreter
+// (still CUDA -- there is no CPU path).
+#include "common.cuh"
+#include "circuit.hpp"
+#include <cuda.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cerrno>
+#include <fstream>
+#include <sstream>
+#include <mutex>
+
+namespace zkb {
+
+namespace {
+
+struct Api {
+  bool ok = false;        // NVRTC usable (compile)
+  bool cu_ok = false;     // driver API usable (load + launch)
+  std::string why, cu_why;
+  decltype(&nvrtcCreateProgram) createProgram;
+  decltype(&nvrtcCompileProgram) compileProgram;
+  decltype(&nvrtcGetCUBINSize) getCUBINSize;
+  decltype(&nvrtcGetCUBIN) getCUBIN;
+  decltype(&nvrtcGetProgramLogSize) getLogSize;
+  decltype(&nvrtcGetProgramLog) getLog;
+  decltype(&nvrtcDestroyProgram) destroyProgram;
+  CUresult (*moduleLoadData)(CUmodule*, const void*);
+  CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*);
+  CUresult (*moduleUnload)(CUmodule);
+  CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+  CUresult (*getErrorString)(CUresult, const char**);
+};
+
+Api& api() {
+  static Api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* rt = nullptr;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) { rt = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (rt) break; }
+    if (!rt) { a.why = "libnvrtc.so.12 not loadable"; return; }
+    bool all = true;
+    auto sym = [&](void* lib, const char* n) { void* p = dlsym(lib, n); if (!p) { all = false; a.why = std::string("missing symbol ") + n; } return p; };
+    a.createProgram = (decltype(a.createProgram))sym(rt, "nvrtcCreateProgram");
+    a.compileProgram = (decltype(a.compileProgram))sym(rt, "nvrtcCompileProgram");
+    a.getCUBINSize = (decltype(a.getCUBINSize))sym(rt, "nvrtcGetCUBINSize");
+    a.getCUBIN = (decltype(a.getCUBIN))sym(rt, "nvrtcGetCUBIN");
+    a.getLogSize = (decltype(a.getLogSize))sym(rt, "nvrtcGetProgramLogSize");
+    a.getLog = (decltype(a.getLog))sym(rt, "nvrtcGetProgramLog");
+    a.destroyProgram = (decltype(a.destroyProgram))sym(rt, "nvrtcDestroyProgram");
+    a.ok = all;
+    void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!cu) { a.cu_why = "libcuda.so.1 not loadable"; return; }
+    all = true;
+    a.moduleLoadData = (decltype(a.moduleLoadData))sym(cu, "cuModuleLoadData");
+    a.moduleGetFunction = (decltype(a.moduleGetFunction))sym(cu, "cuModuleGetFunction");
+    a.moduleUnload = (decltype(a.moduleUnload))sym(cu, "cuModuleUnload");
+    a.launchKernel = (decltype(a.launchKernel))sym(cu, "cuLaunchKernel");
+    a.getErrorString = (decltype(a.getErrorString))sym(cu, "cuGetErrorString");
+    a.cu_ok = all;
+    if (!all) a.cu_why = a.why;
+  });
+  return a;
+}
+
+constexpr int JIT_BLOCK = 128;
+
+const char* PREAMBLE = R"(
+typedef unsigned int u32; typedef unsigned long long u64;
+#define P 2013265921u
+#define NB 1073741848u   /* Montgomery form of -11 (Fp4 = Fp[x]/(x^4+11)) */
+__device__ __forceinline__ u32 red(u32 x) { return min(x, x - P); }
+__device__ __forceinline__ u32 mull(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x77ffffffu; return (u32)((t + (u64)m * P) >> 32); }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { return red(mull(a, b)); }
+__device__ __forceinline__ u32 add(u32 a, u32 b) { return red(a + b); }
+__device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return min(d, d + P); }
+struct F4 { u32 a, b, c, d; };
+__device__ __forceinline__ F4 mul4(F4 x, F4 y) {
+  F4 r;
+  r.a = add(mul(x.a, y.a), mul(NB, add(add(mul(x.b, y.d), mul(x.c, y.c)), mul(x.d, y.b))));
+  r.b = add(add(mul(x.a, y.b), mul(x.b, y.a)), mul(NB, add(mul(x.c, y.d), mul(x.d, y.c))));
+  r.c = add(add(add(mul(x.a, y.c), mul(x.b, y.b)), mul(x.c, y.a)), mul(NB, mul(x.d, y.d)));
+  r.d = add(add(add(mul(x.a, y.d), mul(x.b, y.c)), mul(x.c, y.b)), mul(x.d, y.a));
+  return r;
+}
+__device__ __forceinline__ F4 ldpw(const uint4* pw, int k) { uint4 w = __ldg(pw + k); F4 r; r.a = w.x; r.b = w.y; r.c = w.z; r.d = w.w; return r; }
+__device__ __forceinline__ F4 scale4(F4 x, u32 s) { F4 r; r.a = mul(x.a, s); r.b = mul(x.b, s); r.c = mul(x.c, s); r.d = mul(x.d, s); return r; }
+__device__ __forceinline__ F4 add4(F4 x, F4 y) { F4 r; r.a = add(x.a, y.a); r.b = add(x.b, y.b); r.c = add(x.c, y.c); r.d = add(x.d, y.d); return r; }
+)";
+
+uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+
+}  // namespace
+
+struct EvalJitKernel {
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  uint32_t n_powers = 1;
+};
+struct EvalJitCache {
+  std::map<uint64_t, EvalJitKernel> kernels;     // keyed by hash of the circuit blob content
+  std::map<uint64_t, bool> failed;
+};
+
+static int min_blocks();
+// Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads.
+static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
+  const size_t n = c.steps.size();
+  // liveness from the returned mix value backwards
+  std::vector<char> fp_used(c.n_fp_vars, 0), mx_used(c.n_mix_vars, 0);
+  std::vector<uint32_t> fp_of(n, 0), mx_of(n, 0);
+  { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) fp_of[i] = fi++; else mx_of[i] = mi++; } }
+  mx_used[c.ret] = 1;
+  for (size_t i = n; i-- > 0;) {
+    const StepDef& s = c.steps[i];
+    switch (s.op) {
+      case PX_ADD: case PX_SUB: case PX_MUL: if (fp_used[fp_of[i]]) fp_used[s.a] = fp_used[s.b] = 1; break;
+      case PX_AND_EQZ: if (mx_used[mx_of[i]]) { mx_used[s.a] = 1; fp_used[s.b] = 1; } break;
+      case PX_AND_COND: if (mx_used[mx_of[i]]) { mx_used[s.a] = mx_used[s.c] = 1; fp_used[s.b] = 1; } break;
+      default: break;
+    }
+  }
+  std::ostringstream o;
+  o << PREAMBLE;
+  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", " << min_blocks() << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
+       "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
+       "  const u32 c = blockIdx.x * " << JIT_BLOCK << "u + threadIdx.x;\n  const size_t dom = (size_t)mask + 1;\n"
+       "#define TAP(g, col, back) __ldg(g + (size_t)(col) * dom + ((c - 4u * (back)) & mask))\n";
+  std::vector<uint32_t> mx_pow(c.n_mix_vars, 0);
+  std::vector<char> mx_zero(c.n_mix_vars, 0);
+  n_powers = 1;
+  uint32_t fi = 0, mi = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const StepDef& s = c.steps[i];
+    if (s.op <= PX_MUL) {
+      uint32_t id = fi++;
+      if (!fp_used[id]) continue;
+      o << "  const u32 f" << id << " = ";
+      switch (s.op) {
+        case PX_CONST: o << Fp::from(s.a).v << "u"; break;
+        case PX_GET: { const TapDef& t = c.taps[s.a]; o << "TAP(g" << t.group << ", " << t.column << ", " << t.back << ")"; break; }
+        case PX_GET_GLOBAL: o << "__ldg(gl + " << (s.a == 0 ? s.b : c.mix_size + s.b) << ")"; break;
+        case PX_ADD: o << "add(f" << s.a << ", f" << s.b << ")"; break;
+        case PX_SUB: o << "sub(f" << s.a << ", f" << s.b << ")"; break;
+        case PX_MUL: o << "mul(f" << s.a << ", f" << s.b << ")"; break;
+      }
+      o << ";\n";
+    } else {
+      uint32_t id = mi++;
+      switch (s.op) {
+        case PX_TRUE: mx_pow[id] = 0; mx_zero[id] = 1; break;
+        case PX_AND_EQZ: {
+          mx_pow[id] = mx_pow[s.a] + 1;
+          if (!mx_used[id]) break;
+          n_powers = std::max(n_powers, mx_pow[s.a] + 1);
+          o << "  const F4 m" << id << " = ";
+          if (mx_zero[s.a]) o << "scale4(ldpw(pw, " << mx_pow[s.a] << "), f" << s.b << ")";
+          else o << "add4(m" << s.a << ", scale4(ldpw(pw, " << mx_pow[s.a] << "), f" << s.b << "))";
+          o << ";\n";
+          break;
+        }
+        case PX_AND_COND: {
+          mx_pow[id] = mx_pow[s.a] + mx_pow[s.c];
+          if (!mx_used[id]) break;
+          n_powers = std::max(n_powers, mx_pow[s.a] + 1);
+          if (mx_zero[s.c]) {         // inner chain is empty: nothing is added
+            if (mx_zero[s.a]) mx_zero[id] = 1; else o << "  const F4 m" << id << " = m" << s.a << ";\n";
+            break;
+          }
+          o << "  const F4 m" << id << " = ";
+          if (mx_zero[s.a]) o << "scale4(mul4(m" << s.c << ", ldpw(pw, " << mx_pow[s.a] << ")), f" << s.b << ")";
+          else o << "add4(m" << s.a << ", scale4(mul4(m" << s.c << ", ldpw(pw, " << mx_pow[s.a] << ")), f" << s.b << "))";
+          o << ";\n";
+          break;
+        }
+      }
+    }
+  }
+  o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
+  if (mx_zero[c.ret]) o << "  F4 r; r.a = r.b = r.c = r.d = 0;\n";
+  else o << "  const F4 r = scale4(m" << c.ret << ", den);\n";
+  o << "  check[c] = r.a; check[dom + c] = r.b; check[2 * dom + c] = r.c; check[3 * dom + c] = r.d;\n}\n";
+  return o.str();
+}
+
+// ZKB_CACHE_DIR, else `_jitcache/` next to libzkb200.so (so that cubins compiled at build time ship with the library),
+// else /tmp/zkb200-cache.
+static std::string cache_dir() {
+  const char* e = getenv("ZKB_CACHE_DIR");
+  if (e && *e) return e;
+  Dl_info info;
+  if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
+    std::string so = info.dli_fname;
+    size_t slash = so.rfind('/');
+    if (slash != std::string::npos) {
+      std::string d = so.substr(0, slash) + "/_jitcache";
+      if (mkdir(d.c_str(), 0777) == 0 || errno == EEXIST) { if (access(d.c_str(), W_OK) == 0) return d; }
+    }
+  }
+  return "/tmp/zkb200-cache";
+}
+static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 16 ? 16 : v; }
+
+static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
+  Api& a = api();
+  const uint64_t key = fnv1a(src);
+  char name[64]; snprintf(name, sizeof name, "/ec_%016llx_sm100a.cubin", (unsigned long long)key);
+  const std::string path = cache_dir() + name;
+  { std::ifstream f(path, std::ios::binary);
+    if (f) { cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>()); if (!cubin.empty()) return true; } }
+  nvrtcProgram prog;
+  if (a.createProgram(&prog, src.c_str(), "zkb_eval_check.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { why = "nvrtcCreateProgram failed"; return false; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--restrict"};
+  nvrtcResult r = a.compileProgram(prog, 4, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t ls = 0; a.getLogSize(prog, &ls);
+    std::string log(ls, '\0'); if (ls) a.getLog(prog, &log[0]);
+    why = "nvrtc compile failed: " + log.substr(0, 600);
+    a.destroyProgram(&prog);
+    return false;
+  }
+  size_t sz = 0; a.getCUBINSize(prog, &sz);
+  cubin.resize(sz); a.getCUBIN(prog, cubin.data());
+  a.destroyProgram(&prog);
+  mkdir(cache_dir().c_str(), 0777);
+  { std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    std::ofstream f(tmp, std::ios::binary);
+    if (f) { f.write(cubin.data(), (std::streamsize)cubin.size()); f.close(); rename(tmp.c_str(), path.c_str()); } }
+  return true;
+}
+
+void eval_jit_free(zkb_ctx* ctx) {
+  if (!ctx->jit) return;
+  EvalJitCache* cache = (EvalJitCache*)ctx->jit;
+  for (auto& kv : cache->kernels) if (kv.second.mod) api().moduleUnload(kv.second.mod);
+  delete cache;
+  ctx->jit = nullptr;
+}
+
+// The generated source (for tests / inspection) -- no device needed.
+std::string eval_jit_source(const CircuitDef& c) { uint32_t np; return generate(c, np); }
+// Compiles the source with NVRTC without loading it (CPU-only check that the generator emits valid CUDA).
+bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
+  Api& a = api();
+  if (!a.ok) { why = a.why; return false; }
+  std::vector<char> cubin; uint32_t np;
+  return compile(generate(c, np), cubin, why);
+}
+
+static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, std::string& why) {
+  Api& a = api();
+  if (!a.ok) { why = a.why; return nullptr; }
+  if (!a.cu_ok) { why = a.cu_why; return nullptr; }
+  if (!ctx->jit) ctx->jit = new EvalJitCache();
+  EvalJitCache* cache = (EvalJitCache*)ctx->jit;
+  uint32_t np = 1;
+  std::string src = generate(c, np);
+  uint64_t key = fnv1a(src);
+  auto it = cache->kernels.find(key);
+  if (it != cache->kernels.end()) return &it->second;
+  if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return nullptr; }
+  std::vector<char> cubin;
+  EvalJitKernel k; k.n_powers = np;
+  if (!compile(src, cubin, why)) { cache->failed[key] = true; return nullptr; }
+  ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
+  CUresult r = a.moduleLoadData(&k.mod, cubin.data());
+  if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
+  if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleLoadData: ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
+  return &(cache->kernels[key] = k);
+}
+
+// Returns false (with `why`) when the JIT path is unavailable; the caller then uses the interpreter.
+bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint32_t* const d_groups[3], const uint32_t* mix_g, const uint32_t* out_g,
+                    const Fp4& poly_mix, int po2, std::string& why) {
+  const EvalJitKernel* k = get_kernel(ctx, c, why);
+  if (!k) return false;
+  const size_t n = (size_t)1 << po2, domain = n * INV_RATE;
+  if (domain < (size_t)JIT_BLOCK) { why = "domain smaller than one block"; return false; }
+  // per-proof data: [powers of poly_mix (4 words each)] [mix globals] [out globals]
+  std::vector<uint32_t> h(4 * (size_t)k->n_powers + c.mix_size + c.out_size + 4);
+  Fp4 cur = Fp4::one();
+  for (uint32_t i = 0; i < k->n_powers; ++i) { cur.store(&h[4 * i]); cur *= poly_mix; }
+  uint32_t* gl = h.data() + 4 * (size_t)k->n_powers;
+  for (uint32_t i = 0; i < c.mix_size; ++i) gl[i] = mix_g[i];
+  for (uint32_t i = 0; i < c.out_size; ++i) gl[c.mix_size + i] = out_g[i];
+  uint32_t* d_data = nullptr;
+  ZKB_CUDA(cudaMallocAsync((void**)&d_data, h.size() * 4, ctx->stream));
+  ZKB_CUDA(cudaMemcpyAsync(d_data, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  Fp w4 = pow(Fp::from(137), (uint64_t)1 << (MAX_ROU_PO2 - 2));
+  Fp three_n = pow(Fp::from(3), n);
+  uint4 invden; uint32_t* idp = &invden.x;
+  Fp wr = Fp::one();
+  for (int r = 0; r < 4; ++r) { idp[r] = inv(three_n * wr - Fp::one()).v; wr *= w4; }
+  const uint32_t* g0 = d_groups[0]; const uint32_t* g1 = d_groups[1]; const uint32_t* g2 = d_groups[2];
+  const uint4* pw = (const uint4*)d_data; const uint32_t* d_gl = d_data + 4 * (size_t)k->n_powers;
+  uint32_t mask = (uint32_t)(domain - 1);
+  void* args[] = {&d_check, &g0, &g1, &g2, &pw, &d_gl, &invden, &mask};
+  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / JIT_BLOCK), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+  if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
+  launched(ctx);
+  ZKB_CUDA(cudaFreeAsync(d_data, ctx->stream));
+  return true;
+}
+
+}  // namespace zkb

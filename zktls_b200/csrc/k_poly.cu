@@ -50,6 +50,34 @@ __global__ void k_bit_reverse(uint32_t* __restrict__ io, int po2, size_t count) 
     col[i] = b; col[r] = a;
   }
 }
+// Tiled in-place bit reversal for po2 >= 2T: write i = (a, m, b) with a the top T bits and b the low T bits; then
+// rev(i) = (rev(b), rev(m), rev(a)), so the 2^T x 2^T tile (a, b) of slice m lands, transposed and with both tile
+// coordinates bit-reversed, in slice rev(m).  One CTA owns the pair of slices {m, rev(m)}: every global access is a row
+// of 2^T consecutive words (128 / 256 bytes) and the permutation itself happens in shared memory.
+template <int T>
+__global__ void __launch_bounds__(256) k_bit_reverse_tiled(uint32_t* __restrict__ io, int po2) {
+  constexpr int W = 1 << T;
+  __shared__ uint32_t A[W][W + 1], B[W][W + 1];
+  const int mid_bits = po2 - 2 * T;
+  const uint32_t m = blockIdx.x & ((1u << mid_bits) - 1u);
+  const uint32_t rm = bit_rev32(m, mid_bits);
+  if (m > rm) return;
+  uint32_t* base = io + ((size_t)(blockIdx.x >> mid_bits) << po2);
+  const int hi_shift = po2 - T;
+  const bool pair = m != rm;
+  for (uint32_t e = threadIdx.x; e < W * W; e += 256) {
+    uint32_t a = e >> T, b = e & (W - 1);
+    A[a][b] = base[((size_t)a << hi_shift) | (m << T) | b];
+    if (pair) B[a][b] = base[((size_t)a << hi_shift) | (rm << T) | b];
+  }
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < W * W; e += 256) {
+    uint32_t a = e >> T, b = e & (W - 1);
+    uint32_t ra = bit_rev32(a, T), rb = bit_rev32(b, T);
+    base[((size_t)a << hi_shift) | (rm << T) | b] = A[rb][ra];
+    if (pair) base[((size_t)a << hi_shift) | (m << T) | b] = B[rb][ra];
+  }
+}
 // io[c][i] *= 3^bitrev(i)
 __global__ void k_zk_shift(uint32_t* __restrict__ io, int po2, size_t count) {
   size_t n = (size_t)1 << po2;
@@ -284,6 +312,14 @@ void batch_expand(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count,
 void batch_bit_reverse(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
   size_t total = count << po2;
   if (!total || po2 == 0) return;
+  if (po2 >= 12 && (count << (po2 - 12)) < (1u << 31)) {
+    k_bit_reverse_tiled<6><<<(unsigned)(count << (po2 - 12)), 256, 0, ctx->stream>>>(io, po2); launched(ctx);
+    return;
+  }
+  if (po2 >= 10 && (count << (po2 - 10)) < (1u << 31)) {
+    k_bit_reverse_tiled<5><<<(unsigned)(count << (po2 - 10)), 256, 0, ctx->stream>>>(io, po2); launched(ctx);
+    return;
+  }
   k_bit_reverse<<<grid_for(total, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(io, po2, count); launched(ctx);
 }
 void zk_shift(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {

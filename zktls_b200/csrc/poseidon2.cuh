@@ -7,17 +7,21 @@
 
 namespace zkb { namespace p2 {
 
-// Montgomery-form constant tables, built at compile time from the canonical values.
+// Constant tables, built at compile time from the canonical values.  Round constants are Montgomery words.  The
+// internal-layer diagonal is kept as PLAIN integers d together with dq = floor(d * 2^32 / P): multiplying a Montgomery
+// word x by the constant d needs no Montgomery reduction -- x * d - mulhi(x, dq) * P lies in [0, 2P) for any 32-bit x
+// (Shoup's precomputed-quotient multiplication), one mul.hi + two mul.lo instead of mul.wide + mul.lo + mul.hi.
 struct ConstTables {
   uint32_t ext[8 * 24];
   uint32_t in[21];
   uint32_t diag[24];
+  uint32_t diag_q[24];
 };
 constexpr ConstTables make_tables() {
   ConstTables t{};
   for (int i = 0; i < 8 * 24; ++i) t.ext[i] = mont_const(RC_EXT_CANON[i]);
   for (int i = 0; i < 21; ++i) t.in[i] = mont_const(RC_INT_CANON[i]);
-  for (int i = 0; i < 24; ++i) t.diag[i] = mont_const(DIAG_CANON[i]);
+  for (int i = 0; i < 24; ++i) { t.diag[i] = (uint32_t)(DIAG_CANON[i] % P); t.diag_q[i] = (uint32_t)(((uint64_t)t.diag[i] << 32) / P); }
   return t;
 }
 constexpr ConstTables HOST_TABLES = make_tables();
@@ -26,6 +30,24 @@ constexpr ConstTables HOST_TABLES = make_tables();
 __constant__ ConstTables c_tables = make_tables();
 #define ZKB_P2_TABLES (::zkb::p2::c_tables)
 #endif
+
+ZKB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// x * d mod P in [0, 2P) for any 32-bit x, given dq = floor(d * 2^32 / P)
+ZKB_HD uint32_t shoup_mul_lazy(uint32_t x, uint32_t d, uint32_t dq) { return x * d - mulhi32(x, dq) * P; }
+// sum of 12 words (each < 2^32) reduced to a canonical element: the 64-bit total is < 12 * 2^32, its high word h <= 11,
+// and 2^32 == R_MOD_P (mod P) with 11 * R_MOD_P < 2P
+ZKB_HD uint32_t sum12(const uint32_t* s) {
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc += s[i];
+  return add_mod(reduce_2p(reduce_2p((uint32_t)acc)), reduce_2p((uint32_t)(acc >> 32) * R_MOD_P));
+}
 
 ZKB_HD uint32_t sbox7(uint32_t x) {
   uint32_t x2 = mont_mul(x, x);
@@ -64,19 +86,18 @@ ZKB_HD void permute(uint32_t* s, const Tables& T) {
     for (int i = 0; i < 24; ++i) s[i] = sbox7(add_mod(s[i], T.ext[r * 24 + i]));
     m_ext(s);
   }
+  // Partial rounds.  Cells are kept LAZY (in [0, 2P)) across these rounds: only cell 0 is made canonical for its
+  // s-box, the row sum is taken over the lazy words, and each cell becomes tot + d_i * s_i with the product reduced
+  // once to [0, P) -- so tot + product < 2P again with no second correction.
 #pragma unroll 1
   for (int r = 0; r < 21; ++r) {
-    s[0] = sbox7(add_mod(s[0], T.in[r]));
-    // tot = sum of all cells; 64-bit accumulate, one reduction
-    uint64_t acc = 0;
+    s[0] = sbox7(add_mod(reduce_2p(s[0]), T.in[r]));
+    uint32_t tot = add_mod(sum12(s), sum12(s + 12));
 #pragma unroll
-    for (int i = 0; i < 24; ++i) acc += s[i];
-    // acc < 24 P < 2^36: fold the high word with 2^32 == R_MOD_P (mod P); hi <= 11 so hi * R_MOD_P < 2P
-    uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
-    uint32_t tot = add_mod(reduce_2p(reduce_2p(lo)), reduce_2p(hi * R_MOD_P));
-#pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = add_mod(tot, mont_mul(T.diag[i], s[i]));
+    for (int i = 0; i < 24; ++i) s[i] = tot + reduce_2p(shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i]));
   }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
 #pragma unroll 1
   for (int r = 4; r < 8; ++r) {
 #pragma unroll

@@ -12,6 +12,7 @@
 #include "ops.cuh"
 #include "poseidon2.cuh"
 #include <memory>
+#include <time.h>
 
 namespace zkb {
 
@@ -135,6 +136,22 @@ struct PolyGroup {
 
 struct FriRound { DevBuf evaluated; DeviceMerkle merkle; size_t domain = 0; };
 
+// ZKB_PROFILE=1: synchronise at every phase boundary of a segment proof and print host-clocked phase times to stderr
+// (diagnostics only; the extra synchronisations cost a little throughput).
+struct PhaseTimer {
+  zkb_ctx* ctx; bool on; double t0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit PhaseTimer(zkb_ctx* c) : ctx(c) { const char* e = getenv("ZKB_PROFILE"); on = e && e[0] == '1'; if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); } }
+  void mark(const char* what) {
+    if (!on) return;
+    double host = now();
+    cudaStreamSynchronize(ctx->stream);
+    double t = now();
+    fprintf(stderr, "zkb200 phase %-28s %8.3f ms (host returned after %8.3f ms)\n", what, t - t0, host - t0);
+    t0 = t;
+  }
+};
+
 }  // namespace zkb
 
 using namespace zkb;
@@ -168,12 +185,17 @@ struct zkb_prover {
 
   // Prover::commit_group: make_coeffs (interpolate + zk_shift), PolyGroup::new, merkle.commit
   void commit_group(int g, const void* trace, bool on_device) {
+    PhaseTimer pt(ctx);
     size_t cols = circuit.group_size[g];
     DevBuf c(ctx, cols * n);
     if (cols) ZKB_CUDA(cudaMemcpyAsync(c.p, trace, cols * n * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    pt.mark("commit_group: upload");
     ntt_inverse(ctx, c.p, cols, po2, true);
+    pt.mark("commit_group: iNTT+zk_shift");
     groups[g].build(ctx, std::move(c), cols, po2);
+    pt.mark("commit_group: LDE+hash+merkle");
     groups[g].merkle.commit(ctx, *iop);
+    pt.mark("commit_group: commit (d2h)");
     roots.push_back(groups[g].merkle.root);
   }
 
@@ -208,16 +230,19 @@ struct zkb_prover {
     const CircuitDef& c = circuit;
     WriteIOP& io_p = *iop;
     const size_t domain = n * INV_RATE;
+    PhaseTimer pt(ctx);
     // 1. check polynomial
     Fp4 poly_mix = io_p.rng.random_ext_elem();
     {
       DevBuf check(ctx, EXT_SIZE * domain);
       const uint32_t* ev[3] = {groups[0].evaluated.p, groups[1].evaluated.p, groups[2].evaluated.p};
       eval_check(ctx, check.p, c, ev, mix.data(), io.data(), poly_mix, po2);
+      pt.mark("finalize: eval_check");
       ntt_inverse(ctx, check.p, EXT_SIZE, po2 + 2, false);
       check_group.build(ctx, std::move(check), CHECK_SIZE, po2);
     }
     check_group.merkle.commit(ctx, io_p);
+    pt.mark("finalize: check group commit");
     roots.push_back(check_group.merkle.root);
     // 2. DEEP evaluations of every tap and of the 16 check polynomials, one device pass + one copy
     Fp4 z = io_p.rng.random_ext_elem();
@@ -239,6 +264,7 @@ struct zkb_prover {
       batch_evaluate_any(ctx, check_group.coeffs.p, po2, d_which.p + tap_size, d_xs.p + 4 * tap_size, d_out.p + 4 * tap_size, CHECK_SIZE);
       d2h(ctx, eval_u.data(), d_out.p, eval_u.size() * 16);
     }
+    pt.mark("finalize: DEEP evaluations");
     // 3. coeff_u: per-register interpolation (host, a few field ops), check evaluations appended
     std::vector<Fp4> coeff_u(tap_size + CHECK_SIZE);
     for (const RegisterDef& r : c.regs) poly_interpolate(&coeff_u[r.tap_pos], &all_xs[r.tap_pos], &eval_u[r.tap_pos], r.size);
@@ -267,6 +293,7 @@ struct zkb_prover {
       }
       mix_poly_coeffs(ctx, combos.p, cur, mix_c, check_group.coeffs.p, d_ids.p + off, CHECK_SIZE, n, (uint32_t)combos_size + 1);
     }
+    pt.mark("finalize: coeff_u + mix_poly_coeffs");
     // 6. subtract the interpolants (touches only the lowest coefficients), then divide on the device
     {
       uint32_t max_sz = 1;
@@ -292,12 +319,14 @@ struct zkb_prover {
       d2h(ctx, rem.data(), d_rem.p, rem.size() * 4);
       for (uint32_t w : rem) ZKB_REQUIRE(w == 0, "combo division left a remainder (inconsistent DEEP evaluations)");
     }
+    pt.mark("finalize: divide");
     // 7. FRI
     DevBuf fin(ctx, EXT_SIZE * n);
     eltwise_sum_extelem(ctx, fin.p, combos.p, n, combos_size + 1);
     combos.reset();
     batch_bit_reverse(ctx, fin.p, EXT_SIZE, po2);
     fri_prove(std::move(fin));
+    pt.mark("finalize: fri_prove + queries");
   }
 
   void fri_prove(DevBuf coeffs) {
