@@ -34,6 +34,7 @@ METRIC = "segments proven/sec (2^20 cycles)"
 UNIT = "segments/s"
 PO2 = 20
 P = 2013265921
+INT32_MODMUL_PEAK = 3.27e12     # measured: tools/ubench/fp64_mix.cu, INT32-only row (11.25 modmul/clk/SM at 1965 MHz)
 
 
 def load_peaks():
@@ -203,8 +204,16 @@ def main():
     def step_device():
         return prover.prove(po2, io, b_code, b_data, b_accum)
 
-    def step_host():
-        return prover.prove(po2, io, h_np[0], h_np[1], h_np[2])
+    def steps_host(k):
+        """k segments from HOST (pinned) buffers through the C-ABI, double-buffered: the 1.17 GB upload of segment i+1 runs on
+        the copy stream while segment i is proven (what a session's queue of continuation segments does).  Every segment's
+        host->device copy and seal read-back happen inside this call."""
+        prover.stage(po2, h_np[0], h_np[1], h_np[2])
+        for i in range(k):
+            if i + 1 < k:
+                prover.stage(po2, h_np[0], h_np[1], h_np[2])
+            s = prover.prove_staged(io)
+        return s
 
     # ---- device-resident arm -----------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank); sampler.start()
@@ -229,12 +238,10 @@ def main():
     value = world * args.steps / (ms_total / 1000.0)
 
     # ---- end-to-end arm: host buffers through the C-ABI prove call ------------------------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        seal_h = step_host()
+    seal_h = steps_host(min(args.warmup, 2))
     barrier()
     hal.timer_start()
-    for _ in range(args.steps):
-        seal_h = step_host()
+    seal_h = steps_host(args.steps)
     ms_e2e = hal.timer_stop()
     barrier()
     t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
@@ -262,8 +269,10 @@ def main():
         perms = rows * ((cols + 15) // 16)
         roof = {"bound": "hbm", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind, "ms_per_launch": ms,
-                "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation",
-                          "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3)}}
+                "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation; peak = measured "
+                                  "pure Montgomery-modmul stream on B200 (profiles/r1_ubench_fp64_mix.txt)",
+                          "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3), "peak_modmul_per_s": INT32_MODMUL_PEAK,
+                          "frac": 1356 * perms / (ms * 1e-3) / INT32_MODMUL_PEAK}}
         del mat, dig
         # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT and x4 LDE over 64 columns of 2^20
         ntt_cols = 64
@@ -294,7 +303,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
                 "config": workload_config(), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
+                        "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if po2 != PO2:
             line["config"]["workload"] = f"DEBUG po2={po2} (not the benchmark config)"

@@ -145,6 +145,12 @@ zkb_err zkb_prover_roots_copy(zkb_prover* p, uint32_t* h_out);
 /* One-shot convenience over the two calls above for traces whose accum group does not depend on `mix`. */
 zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const void* code, const void* data, const void* accum,
                           int traces_on_device);
+/* Pipelined form for a queue of segments (the continuation segments of one session): zkb_prover_stage_traces starts the
+ * host->device copy of a segment's three trace groups (pinned host memory recommended) on a separate copy stream into one of
+ * two staging slots and returns at once; zkb_prove_staged proves the oldest staged segment (as zkb_prove_segment does).
+ * Staging segment k+1 before proving segment k overlaps its upload with the proof.  At most two segments may be staged. */
+zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, const void* h_data, const void* h_accum);
+zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io);
 /* CPU verifier for a seal produced by the prover (risc0-zkp verify/*): checks the transcript, Merkle paths, FRI
  * and the constraint relation at the DEEP point.  Host-only, like the reference's verifier. */
 zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words);

@@ -76,3 +76,30 @@ def test_eval_check_matches_oracle(hal, oracle, po2):
     chk = hal.alloc_elem(4 * dom)
     hal.eval_check(chk, blob, hal.copy_from_elem(accum), hal.copy_from_elem(code), hal.copy_from_elem(data), mix, out, pm, po2)
     assert np.array_equal(chk.to_numpy(), oracle.eval_check(blob, accum, code, data, mix, out, pm, po2))
+
+
+def test_staged_pipeline_gives_the_same_seals(hal, oracle):
+    """zkb_prover_stage_traces / zkb_prove_staged (double-buffered upload) must produce the seals of the plain call, in order."""
+    from zktls_b200.prover import SegmentProver
+    blob = circuit.syn_circuit(**SMALL).blob()
+    gp = SegmentProver(hal, blob)
+    segs = [synth.trace_a(SMALL, 9, 40 + i) for i in range(4)]
+    want = []
+    for io, code, data, accum in segs:
+        op = oracle.Prover(blob); op.begin(9, io, code, data); want.append(op.finish(accum))
+    got = []
+    gp.stage(9, *segs[0][1:])
+    for i in range(len(segs)):
+        if i + 1 < len(segs):
+            gp.stage(9, *segs[i + 1][1:])
+        got.append(gp.prove_staged(segs[i][0]))
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    # misuse is an error string, not a crash
+    from zktls_b200 import ZkbError
+    with pytest.raises(ZkbError):
+        gp.prove_staged(segs[0][0])
+    gp.stage(9, *segs[0][1:]); gp.stage(9, *segs[1][1:])
+    with pytest.raises(ZkbError):
+        gp.stage(9, *segs[2][1:])
+    gp.close()

@@ -216,29 +216,49 @@ __global__ void k_eval_reduce(uint4* __restrict__ out, const uint4* __restrict__
 // Recurrence: next = z*cur + p[i]; p[i] = cur  (i descending).  Parallelised by chunks of DIV_CHUNK: pass 1 computes
 // each chunk's Horner total, the totals are divided recursively by (X - z^DIV_CHUNK) -- which yields exactly every
 // chunk's carry-in and the global remainder -- and pass 2 replays each chunk from its carry.
-constexpr int DIV_CHUNK = 64;
-__global__ void k_div_totals(uint4* __restrict__ totals, const uint4* __restrict__ p, size_t n, Fp4Arg z_arg) {
+constexpr int DIV_CHUNK = 8;      // 8 Fp4 = one 128-byte line per thread; n/8 threads keep the SMs full, 7 levels for n = 2^20
+__global__ void __launch_bounds__(128) k_div_totals(uint4* __restrict__ totals, const uint4* __restrict__ p, size_t n, Fp4Arg z_arg) {
   size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = c * DIV_CHUNK;
   if (lo >= n) return;
-  size_t hi = min(lo + (size_t)DIV_CHUNK, n);
   Fp4 z = arg4(z_arg), acc;
-  for (size_t i = hi; i-- > lo;) { uint4 v = p[i]; acc = acc * z + ld4(v); }
+  if (lo + DIV_CHUNK <= n) {
+    uint4 v[DIV_CHUNK];
+#pragma unroll
+    for (int k = 0; k < DIV_CHUNK; ++k) v[k] = p[lo + k];
+#pragma unroll
+    for (int k = DIV_CHUNK - 1; k >= 0; --k) acc = acc * z + ld4(v[k]);
+  } else {
+    for (size_t i = n; i-- > lo;) { uint4 v = p[i]; acc = acc * z + ld4(v); }
+  }
   totals[c] = st4(acc);
 }
-__global__ void k_div_apply(uint4* __restrict__ p, const uint4* __restrict__ carries, size_t n, Fp4Arg z_arg) {
+__global__ void __launch_bounds__(128) k_div_apply(uint4* __restrict__ p, const uint4* __restrict__ carries, size_t n, Fp4Arg z_arg) {
   size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = c * DIV_CHUNK;
   if (lo >= n) return;
-  size_t hi = min(lo + (size_t)DIV_CHUNK, n);
   Fp4 z = arg4(z_arg);
   uint4 cv = carries[c];
   Fp4 cur = ld4(cv);
-  for (size_t i = hi; i-- > lo;) {
-    uint4 v = p[i];
-    Fp4 next = z * cur + ld4(v);
-    p[i] = st4(cur);
-    cur = next;
+  if (lo + DIV_CHUNK <= n) {
+    uint4 v[DIV_CHUNK];
+#pragma unroll
+    for (int k = 0; k < DIV_CHUNK; ++k) v[k] = p[lo + k];
+#pragma unroll
+    for (int k = DIV_CHUNK - 1; k >= 0; --k) {
+      Fp4 next = z * cur + ld4(v[k]);
+      v[k] = st4(cur);
+      cur = next;
+    }
+#pragma unroll
+    for (int k = 0; k < DIV_CHUNK; ++k) p[lo + k] = v[k];
+  } else {
+    for (size_t i = n; i-- > lo;) {
+      uint4 v = p[i];
+      Fp4 next = z * cur + ld4(v);
+      p[i] = st4(cur);
+      cur = next;
+    }
   }
 }
 __global__ void k_div_serial(uint4* __restrict__ p, size_t n, Fp4Arg z_arg, uint4* __restrict__ rem) {
@@ -357,7 +377,7 @@ void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uin
 }
 // d_work: caller-provided device scratch of >= 2 * ceil(n / DIV_CHUNK) Fp4 (or nullptr to use a temporary)
 void poly_divide(zkb_ctx* ctx, uint32_t* d_poly, size_t n, const Fp4& z, uint32_t* d_rem) {
-  if (n <= 4 * DIV_CHUNK) {
+  if (n <= 64) {
     k_div_serial<<<1, 32, 0, ctx->stream>>>((uint4*)d_poly, n, to_arg(z), (uint4*)d_rem); launched(ctx);
     return;
   }

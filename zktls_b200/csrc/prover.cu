@@ -175,6 +175,64 @@ struct zkb_prover {
   std::vector<uint32_t> io, mix;
   bool begun = false, finished = false;
 
+  // Double-buffered trace staging: segment k+1's host->device copy runs on `copy_stream` while segment k is proven on the
+  // ctx stream (zkb_prover_stage_traces / zkb_prove_staged).
+  struct TraceSlot {
+    uint32_t* buf[3] = {nullptr, nullptr, nullptr};
+    size_t words[3] = {0, 0, 0};
+    cudaEvent_t uploaded = nullptr, consumed = nullptr;
+    int po2 = -1;
+    bool full = false;
+  };
+  TraceSlot slots[2];
+  cudaStream_t copy_stream = nullptr;
+  int stage_idx = 0, prove_idx = 0;
+
+  void stage_traces(int po2_, const void* const h_traces[3]) {
+    ZKB_REQUIRE(po2_ >= 6 && po2_ + 2 <= MAX_PO2, "segment po2 out of range [6, 24]");
+    if (!copy_stream) ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    TraceSlot& sl = slots[stage_idx];
+    ZKB_REQUIRE(!sl.full, "both staging slots are full: call zkb_prove_staged first");
+    if (!sl.uploaded) {
+      ZKB_CUDA(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+      ZKB_CUDA(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+    } else {
+      ZKB_CUDA(cudaStreamWaitEvent(copy_stream, sl.consumed, 0));    // the proof that last read this slot must be done with it
+    }
+    const size_t rows = (size_t)1 << po2_;
+    for (int g = 0; g < 3; ++g) {
+      size_t words = (size_t)circuit.group_size[g] * rows;
+      if (sl.words[g] < words) {
+        if (sl.buf[g]) { ZKB_CUDA(cudaStreamSynchronize(ctx->stream)); ZKB_CUDA(cudaStreamSynchronize(copy_stream)); ZKB_CUDA(cudaFree(sl.buf[g])); }
+        ZKB_CUDA(cudaMalloc((void**)&sl.buf[g], std::max<size_t>(words, 4) * 4));
+        sl.words[g] = words;
+      }
+      if (words) ZKB_CUDA(cudaMemcpyAsync(sl.buf[g], h_traces[g], words * 4, cudaMemcpyHostToDevice, copy_stream));
+    }
+    ZKB_CUDA(cudaEventRecord(sl.uploaded, copy_stream));
+    sl.po2 = po2_; sl.full = true;
+    stage_idx ^= 1;
+  }
+  void prove_staged(const uint32_t* h_io) {
+    TraceSlot& sl = slots[prove_idx];
+    ZKB_REQUIRE(sl.full, "no staged traces: call zkb_prover_stage_traces first");
+    ZKB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0));
+    segment_begin(sl.po2, h_io, sl.buf[GROUP_CODE], sl.buf[GROUP_DATA], true, nullptr);
+    segment_finish(sl.buf[GROUP_ACCUM], true);
+    ZKB_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
+    sl.full = false;
+    prove_idx ^= 1;
+  }
+  void free_staging() {
+    for (TraceSlot& sl : slots) {
+      for (int g = 0; g < 3; ++g) { if (sl.buf[g]) cudaFree(sl.buf[g]); sl.buf[g] = nullptr; sl.words[g] = 0; }
+      if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+      if (sl.consumed) cudaEventDestroy(sl.consumed);
+      sl = TraceSlot();
+    }
+    if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
+  }
+
   void reset() {
     iop.reset(new WriteIOP());
     for (auto& g : groups) g = PolyGroup();
@@ -432,7 +490,7 @@ zkb_err zkb_prover_new(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_w
 }
 zkb_err zkb_prover_free(zkb_prover* p) {
   ZKB_API_BEGIN
-  if (p) { use(p->ctx); p->reset(); cudaStreamSynchronize(p->ctx->stream); delete p; }
+  if (p) { use(p->ctx); p->reset(); cudaStreamSynchronize(p->ctx->stream); if (p->copy_stream) cudaStreamSynchronize(p->copy_stream); p->free_staging(); delete p; }
   ZKB_API_END
 }
 zkb_err zkb_prover_segment_begin(zkb_prover* p, int po2, const uint32_t* h_io, const void* code, const void* data, int traces_on_device, uint32_t* h_mix_out) {
@@ -457,6 +515,24 @@ zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const vo
   use(p->ctx);
   p->segment_begin(po2, h_io, code, data, traces_on_device != 0, nullptr);
   p->segment_finish(accum, traces_on_device != 0);
+  ZKB_API_END
+}
+zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, const void* h_data, const void* h_accum) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(p != nullptr, "null prover");
+  use(p->ctx);
+  const void* tr[3];
+  tr[GROUP_ACCUM] = h_accum; tr[GROUP_CODE] = h_code; tr[GROUP_DATA] = h_data;
+  for (int g = 0; g < 3; ++g) ZKB_REQUIRE(tr[g] || p->circuit.group_size[g] == 0, "null trace");
+  p->stage_traces(po2, tr);
+  ZKB_API_END
+}
+zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(p != nullptr, "null prover");
+  use(p->ctx);
+  ZKB_REQUIRE(h_io || p->circuit.out_size == 0, "null io");
+  p->prove_staged(h_io);
   ZKB_API_END
 }
 zkb_err zkb_prover_seal_words(zkb_prover* p, size_t* out) {

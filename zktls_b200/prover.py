@@ -55,6 +55,19 @@ class SegmentProver:
         check(lib().zkb_prove_segment(self.h, C.c_int(po2), _hp(io), self._ptr(c, cd), self._ptr(d, dd), self._ptr(a, ad), C.c_int(int(cd))))
         return self.seal()
 
+    def stage(self, po2, code, data, accum):
+        """Starts the asynchronous upload of one segment's host traces (numpy arrays, ideally over pinned memory) into a
+        staging slot; returns immediately.  The arrays must stay alive and unmodified until the matching prove_staged()."""
+        arrs = [np.ascontiguousarray(t, dtype=np.uint32) for t in (code, data, accum)]
+        self._staged = getattr(self, "_staged", []) + [arrs]
+        check(lib().zkb_prover_stage_traces(self.h, C.c_int(po2), *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+
+    def prove_staged(self, io):
+        io = np.ascontiguousarray(io, dtype=np.uint32)
+        check(lib().zkb_prove_staged(self.h, _hp(io)))
+        self._staged.pop(0)
+        return self.seal()
+
     def seal(self):
         n = C.c_size_t(); check(lib().zkb_prover_seal_words(self.h, C.byref(n)))
         s = np.zeros(n.value, np.uint32); check(lib().zkb_prover_seal_copy(self.h, _hp(s))); return s
