@@ -98,8 +98,8 @@ def cpu_baseline(sample_po2, threads=None):
     """The oracle prover (restated CpuHal) on a SYN-280 segment of 2^sample_po2 cycles, all host threads."""
     from zktls_b200 import circuit, synth
     from oracle import oracle as O
-    if threads:
-        O.lib().orc_set_num_threads(int(threads))
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    O.lib().orc_set_num_threads(int(threads) if threads else (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()))
     cores = O.lib().orc_num_threads()
     blob = circuit.syn_circuit(**circuit.SYN280).blob()
     io, code, data, accum = synth.trace_a(circuit.SYN280, sample_po2, 0xB200)

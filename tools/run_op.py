@@ -14,10 +14,14 @@ elif a.op == "merkle":
     for _ in range(a.reps): hal.merkle_build(d, rows)
 elif a.op == "intt":
     b = hal.alloc_elem(a.cols * n)
+    hal.batch_interpolate_ntt_zk_shift(b, a.cols); hal.sync(); hal.timer_start()
     for _ in range(a.reps): hal.batch_interpolate_ntt_zk_shift(b, a.cols)
+    ms = hal.timer_stop() / a.reps; print(f"intt+shift {a.cols} x 2^{a.po2}: {ms:.3f} ms  {8 * n * a.cols / ms / 1e6:.0f} GB/s  env", {k: v for k, v in os.environ.items() if k.startswith("ZKB_")})
 elif a.op == "lde":
     b = hal.alloc_elem(a.cols * n); o = hal.alloc_elem(a.cols * 4 * n)
+    hal.batch_expand_into_evaluate_ntt(o, b, a.cols, 2); hal.sync(); hal.timer_start()
     for _ in range(a.reps): hal.batch_expand_into_evaluate_ntt(o, b, a.cols, 2)
+    ms = hal.timer_stop() / a.reps; print(f"lde x4 {a.cols} x 2^{a.po2}: {ms:.3f} ms  {20 * n * a.cols / ms / 1e6:.0f} GB/s  env", {k: v for k, v in os.environ.items() if k.startswith("ZKB_")})
 elif a.op == "eval_check":
     import os
     from zktls_b200 import circuit

@@ -1,5 +1,5 @@
 // Tiled BabyBear NTT / iNTT / LDE kernels (sm_100a): register radix-16 butterflies, shared-memory exchanges,
-// four-step passes sized so that a whole batch of columns stays in the 126 MB L2 between passes.
+// four-step passes (one strided, one contiguous for n <= 2^22).
 //
 // Index conventions are those of risc0-zkp `core/ntt.rs`, decomposed as follows.  Write a
 // position of the 2^k array as p = p1 * S + p2 (S = 2^s) and the coefficient index it holds in bit-reversed layout as
@@ -16,8 +16,9 @@
 // Each thread keeps 16 elements in registers and runs up to four butterfly levels on them; between such rounds the
 // CTA's tile goes through shared memory (padded by one word per 16 so that every round's access pattern is
 // bank-conflict free).  Pass C works on 4096 contiguous elements per CTA (128-bit global accesses on the
-// consecutive-16 side, 128-byte lines on the strided side); pass S works on a (2^a x T) tile whose rows are T >= 16
-// consecutive elements (>= 64-byte segments).  Per-level twiddles w_{2^(q+1)}^x come from an 8192-word table that
+// consecutive-16 side, 128-byte lines on the strided side); pass S works on a (2^a x T) tile whose rows are T >= 8
+// consecutive elements (whole 32-byte sectors; T = 8 for a >= 9 so that two 512-thread CTAs share an SM and overlap each
+// other's load / compute / store phases -- 14 % faster than one 1024-thread CTA with T = 16).  Per-level twiddles w_{2^(q+1)}^x come from an 8192-word table that
 // stays in L1; the inter-pass twiddles are generated per thread as a running product G^m from two table look-ups.
 #include "common.cuh"
 #include "ntt.cuh"
@@ -178,11 +179,15 @@ struct SArgs {
   uint32_t use_table;      // inverse only: multiply V by table[rev_{A-4}(t')] (includes the 1/n scale where needed)
 };
 
-template <int A> struct STile { static constexpr int T_LOG = (A >= 8) ? 4 : (12 - A); static constexpr int T = 1 << T_LOG; static constexpr int THREADS = (1 << A) * T / 16; };
+// TL = log2 of the tile width (consecutive elements per row); 0 = default: 16 columns for A >= 8, else a 4096-element tile.
+template <int A, int TL = 0> struct STile {
+  static constexpr int T_LOG = TL ? TL : ((A >= 8) ? 4 : (12 - A));
+  static constexpr int T = 1 << T_LOG; static constexpr int THREADS = (1 << A) * T / 16;
+};
 
-template <int A, bool INV>
-__global__ void __launch_bounds__(STile<A>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args) {
-  constexpr int T_LOG = STile<A>::T_LOG, T = STile<A>::T, TPB = (1 << A) / 16;
+template <int A, bool INV, int TL = 0>
+__global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args) {
+  constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
   extern __shared__ uint32_t sm[];
   const uint32_t tid = threadIdx.x;
   const uint32_t c2 = tid & (T - 1), t = tid >> T_LOG;                      // column inside the tile, thread inside the column
@@ -310,17 +315,18 @@ static bool make_plan(int k, Plan& pl) {
   return false;
 }
 
-template <int A, bool INV>
+template <int A, bool INV, int TL = 0>
 static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
-  using ST = STile<A>;
+  using ST = STile<A, TL>;
   SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
   size_t tile_elems = (size_t)(1 << A) * ST::T;
   size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
-  auto kern = k_ntt_s<A, INV>;
+  auto kern = k_ntt_s<A, INV, TL>;
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args);
   launched(ctx);
 }
+static int s_tile_log() { static int v = [] { const char* e = getenv("ZKB_NTT_S_TLOG"); return e ? atoi(e) : 3; }(); return v; }
 template <bool INV>
 static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
   switch (a) {
@@ -329,8 +335,16 @@ static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_lo
     case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
     case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
     case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
-    case 9: launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
-    case 10: launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
+    case 9:
+      if (s_tile_log() == 3) launch_s<9, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      else if (s_tile_log() == 2) launch_s<9, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      else launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      break;
+    case 10:
+      if (s_tile_log() == 3) launch_s<10, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      else if (s_tile_log() == 2) launch_s<10, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      else launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g);
+      break;
     default: throw Error("zkb200: unsupported strided NTT size");
   }
 }
@@ -351,9 +365,12 @@ static void dispatch_c_fwd(zkb_ctx* ctx, int a, uint32_t* out, const uint32_t* i
   launched(ctx);
 }
 
-// columns per batch so that the batch (in + out) stays L2-resident between passes
+// Columns per launch.  Measured on B200 (profiles/r1_e_ntt_sweep.txt): the passes are INT32-pipe bound, not HBM bound, so
+// keeping a batch L2-resident between passes buys nothing while small launches lose to tails -- the default is the whole
+// group in one launch per pass (LDE of 224 x 2^20: 8.0 ms with 48 MB batches, 5.8 ms unbatched).  ZKB_NTT_L2_BYTES
+// restores batching for experiments.
 static size_t batch_columns(size_t count, size_t bytes_per_column) {
-  static size_t budget = [] { const char* e = getenv("ZKB_NTT_L2_BYTES"); return e ? (size_t)atoll(e) : (size_t)48 << 20; }();
+  static size_t budget = [] { const char* e = getenv("ZKB_NTT_L2_BYTES"); return e ? (size_t)atoll(e) : (size_t)1 << 40; }();
   size_t b = std::max<size_t>(1, budget / std::max<size_t>(bytes_per_column, 1));
   size_t gran = std::max<size_t>(1, ((size_t)TILE * 4) / std::max<size_t>(bytes_per_column, 1));   // whole tiles per batch
   if (b >= count) return count;
