@@ -45,6 +45,8 @@ struct Api {
   CUresult (*moduleUnload)(CUmodule);
   CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
   CUresult (*getErrorString)(CUresult, const char**);
+  CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+  CUresult (*memcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
 };
 
 Api& api() {
@@ -72,6 +74,8 @@ Api& api() {
     a.moduleUnload = (decltype(a.moduleUnload))sym(cu, "cuModuleUnload");
     a.launchKernel = (decltype(a.launchKernel))sym(cu, "cuLaunchKernel");
     a.getErrorString = (decltype(a.getErrorString))sym(cu, "cuGetErrorString");
+    a.moduleGetGlobal = (decltype(a.moduleGetGlobal))sym(cu, "cuModuleGetGlobal_v2");
+    a.memcpyHtoDAsync = (decltype(a.memcpyHtoDAsync))sym(cu, "cuMemcpyHtoDAsync_v2");
     a.cu_ok = all;
     if (!all) a.cu_why = a.why;
   });
@@ -98,7 +102,13 @@ __device__ __forceinline__ F4 mul4(F4 x, F4 y) {
   r.d = add(add(add(mul(x.a, y.d), mul(x.b, y.c)), mul(x.c, y.b)), mul(x.d, y.a));
   return r;
 }
-__device__ __forceinline__ F4 ldpw(const uint4* pw, int k) { uint4 w = __ldg(pw + k); F4 r; r.a = w.x; r.b = w.y; r.c = w.z; r.d = w.w; return r; }
+__device__ __forceinline__ F4 tof4(uint4 w) { F4 r; r.a = w.x; r.b = w.y; r.c = w.z; r.d = w.w; return r; }
+// Lazy accumulation of sum_k pw_k * f_k (pw_k, f_k canonical): a 64-bit accumulator per Fp4 component takes one
+// IMAD.WIDE per term; after every second term its high word is brought back below P (one VIADDMNMX), which keeps the
+// accumulator below P * 2^32 + 2 P^2 < 2^64; a single Montgomery reduction at the end of the chain gives the canonical
+// word.  An accumulator that continues from a canonical value m starts as m << 32 (= m * R).
+__device__ __forceinline__ u64 fixhi(u64 a) { u32 hi = (u32)(a >> 32); hi = min(hi, hi - P); return ((u64)hi << 32) | (u32)a; }
+__device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x77ffffffu; return red((u32)((a + (u64)m * P) >> 32)); }
 __device__ __forceinline__ F4 scale4(F4 x, u32 s) { F4 r; r.a = mul(x.a, s); r.b = mul(x.b, s); r.c = mul(x.c, s); r.d = mul(x.d, s); return r; }
 __device__ __forceinline__ F4 add4(F4 x, F4 y) { F4 r; r.a = add(x.a, y.a); r.b = add(x.b, y.b); r.c = add(x.c, y.c); r.d = add(x.d, y.d); return r; }
 )";
@@ -115,6 +125,8 @@ struct EvalJitKernel {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   uint32_t n_powers = 1;
+  CUdeviceptr cdata = 0;        // __constant__ zkb_cd (per-proof powers + globals) when the circuit's data fits in 64 KB
+  size_t cdata_bytes = 0;
 };
 struct EvalJitCache {
   std::map<uint64_t, EvalJitKernel> kernels;     // keyed by hash of the circuit blob content
@@ -122,6 +134,11 @@ struct EvalJitCache {
 };
 
 static int min_blocks();
+// Per-proof kernel data: [powers of poly_mix, 4 words each][mix globals][out globals].  It lives in the module's
+// __constant__ bank when it fits (operands then come straight from the constant cache), else behind a pointer.
+constexpr size_t CONST_WORDS_MAX = 15 * 1024;
+static bool const_mode(const CircuitDef& c, uint32_t n_powers) { return 4 * (size_t)n_powers + c.mix_size + c.out_size <= CONST_WORDS_MAX; }
+
 // Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads.
 static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
   const size_t n = c.steps.size();
@@ -139,15 +156,44 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
       default: break;
     }
   }
+  // how each live mix value is consumed: as the base of a following AndEqz (chainable), or otherwise (needs a canonical F4)
+  std::vector<uint32_t> eqz_uses(c.n_mix_vars, 0), other_uses(c.n_mix_vars, 0);
+  std::vector<uint32_t> mx_pow(c.n_mix_vars, 0);
+  n_powers = 1;
+  {
+    uint32_t mi = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const StepDef& s = c.steps[i];
+      if (s.op <= PX_MUL) continue;
+      uint32_t id = mi++;
+      if (s.op == PX_AND_EQZ) { mx_pow[id] = mx_pow[s.a] + 1; if (mx_used[id]) { ++eqz_uses[s.a]; n_powers = std::max(n_powers, mx_pow[s.a] + 1); } }
+      else if (s.op == PX_AND_COND) { mx_pow[id] = mx_pow[s.a] + mx_pow[s.c]; if (mx_used[id]) { ++other_uses[s.a]; ++other_uses[s.c]; n_powers = std::max(n_powers, mx_pow[s.a] + 1); } }
+    }
+    ++other_uses[c.ret];
+  }
+  const bool cm = const_mode(c, n_powers);
+  const size_t gl_off = 4 * (size_t)n_powers;
   std::ostringstream o;
   o << PREAMBLE;
+  if (cm) {
+    o << "__constant__ u32 zkb_cd[" << std::max<size_t>(gl_off + c.mix_size + c.out_size, 4) << "];\n"
+         "#define PW(k) make_uint4(zkb_cd[4 * (k)], zkb_cd[4 * (k) + 1], zkb_cd[4 * (k) + 2], zkb_cd[4 * (k) + 3])\n"
+         "#define GL(i) zkb_cd[" << gl_off << " + (i)]\n";
+  } else {
+    o << "#define PW(k) __ldg(pw + (k))\n#define GL(i) __ldg(gl + (i))\n";
+  }
   o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", " << min_blocks() << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
        "  const u32 c = blockIdx.x * " << JIT_BLOCK << "u + threadIdx.x;\n  const size_t dom = (size_t)mask + 1;\n"
        "#define TAP(g, col, back) __ldg(g + (size_t)(col) * dom + ((c - 4u * (back)) & mask))\n";
-  std::vector<uint32_t> mx_pow(c.n_mix_vars, 0);
-  std::vector<char> mx_zero(c.n_mix_vars, 0);
-  n_powers = 1;
+  enum { ST_ZERO = 0, ST_CANON = 1, ST_ACC = 2 };
+  std::vector<char> state(c.n_mix_vars, ST_ZERO);
+  std::vector<uint32_t> acc_set(c.n_mix_vars, 0), acc_terms(c.n_mix_vars, 0);
+  auto materialize = [&](uint32_t id) {      // accumulators of `id` -> canonical F4 m<id>
+    uint32_t a = acc_set[id];
+    o << "  F4 m" << id << "; m" << id << ".a = fin(A" << a << "_0); m" << id << ".b = fin(A" << a << "_1); m" << id << ".c = fin(A" << a << "_2); m" << id << ".d = fin(A" << a << "_3);\n";
+    state[id] = ST_CANON;
+  };
   uint32_t fi = 0, mi = 0;
   for (size_t i = 0; i < n; ++i) {
     const StepDef& s = c.steps[i];
@@ -158,45 +204,60 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
       switch (s.op) {
         case PX_CONST: o << Fp::from(s.a).v << "u"; break;
         case PX_GET: { const TapDef& t = c.taps[s.a]; o << "TAP(g" << t.group << ", " << t.column << ", " << t.back << ")"; break; }
-        case PX_GET_GLOBAL: o << "__ldg(gl + " << (s.a == 0 ? s.b : c.mix_size + s.b) << ")"; break;
+        case PX_GET_GLOBAL: o << "GL(" << (s.a == 0 ? s.b : c.mix_size + s.b) << ")"; break;
         case PX_ADD: o << "add(f" << s.a << ", f" << s.b << ")"; break;
         case PX_SUB: o << "sub(f" << s.a << ", f" << s.b << ")"; break;
         case PX_MUL: o << "mul(f" << s.a << ", f" << s.b << ")"; break;
       }
       o << ";\n";
-    } else {
-      uint32_t id = mi++;
-      switch (s.op) {
-        case PX_TRUE: mx_pow[id] = 0; mx_zero[id] = 1; break;
-        case PX_AND_EQZ: {
-          mx_pow[id] = mx_pow[s.a] + 1;
-          if (!mx_used[id]) break;
-          n_powers = std::max(n_powers, mx_pow[s.a] + 1);
-          o << "  const F4 m" << id << " = ";
-          if (mx_zero[s.a]) o << "scale4(ldpw(pw, " << mx_pow[s.a] << "), f" << s.b << ")";
-          else o << "add4(m" << s.a << ", scale4(ldpw(pw, " << mx_pow[s.a] << "), f" << s.b << "))";
-          o << ";\n";
-          break;
-        }
-        case PX_AND_COND: {
-          mx_pow[id] = mx_pow[s.a] + mx_pow[s.c];
-          if (!mx_used[id]) break;
-          n_powers = std::max(n_powers, mx_pow[s.a] + 1);
-          if (mx_zero[s.c]) {         // inner chain is empty: nothing is added
-            if (mx_zero[s.a]) mx_zero[id] = 1; else o << "  const F4 m" << id << " = m" << s.a << ";\n";
-            break;
-          }
-          o << "  const F4 m" << id << " = ";
-          if (mx_zero[s.a]) o << "scale4(mul4(m" << s.c << ", ldpw(pw, " << mx_pow[s.a] << ")), f" << s.b << ")";
-          else o << "add4(m" << s.a << ", scale4(mul4(m" << s.c << ", ldpw(pw, " << mx_pow[s.a] << ")), f" << s.b << "))";
-          o << ";\n";
-          break;
-        }
-      }
+      continue;
     }
+    uint32_t id = mi++;
+    if (s.op == PX_TRUE) { state[id] = ST_ZERO; continue; }
+    if (!mx_used[id]) continue;
+    if (s.op == PX_AND_EQZ) {
+      const uint32_t base = s.a, k = mx_pow[base];
+      uint32_t set, terms;
+      if (state[base] == ST_ACC && eqz_uses[base] == 1 && other_uses[base] == 0) {          // continue the chain in place
+        set = acc_set[base]; terms = acc_terms[base];
+        o << "  { const uint4 w = PW(" << k << "); A" << set << "_0 += (u64)f" << s.b << " * w.x; A" << set << "_1 += (u64)f" << s.b << " * w.y; A" << set
+          << "_2 += (u64)f" << s.b << " * w.z; A" << set << "_3 += (u64)f" << s.b << " * w.w; }\n";
+        ++terms;
+      } else {
+        set = id;
+        if (state[base] == ST_ACC) materialize(base);       // (cannot happen: multi-use values are materialised at definition)
+        if (state[base] == ST_ZERO) {
+          o << "  u64 A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = (u64)f" << s.b
+            << " * w.x; A" << set << "_1 = (u64)f" << s.b << " * w.y; A" << set << "_2 = (u64)f" << s.b << " * w.z; A" << set << "_3 = (u64)f" << s.b << " * w.w; }\n";
+        } else {
+          o << "  u64 A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = ((u64)m" << base
+            << ".a << 32) + (u64)f" << s.b << " * w.x; A" << set << "_1 = ((u64)m" << base << ".b << 32) + (u64)f" << s.b << " * w.y; A" << set << "_2 = ((u64)m" << base
+            << ".c << 32) + (u64)f" << s.b << " * w.z; A" << set << "_3 = ((u64)m" << base << ".d << 32) + (u64)f" << s.b << " * w.w; }\n";
+        }
+        terms = 1;
+      }
+      if (terms == 2) {
+        o << "  A" << set << "_0 = fixhi(A" << set << "_0); A" << set << "_1 = fixhi(A" << set << "_1); A" << set << "_2 = fixhi(A" << set << "_2); A" << set << "_3 = fixhi(A" << set << "_3);\n";
+        terms = 0;
+      }
+      state[id] = ST_ACC; acc_set[id] = set; acc_terms[id] = terms;
+      if (!(eqz_uses[id] == 1 && other_uses[id] == 0)) materialize(id);
+      continue;
+    }
+    // PX_AND_COND: m_id = m_a + f_b * (m_c (x) poly_mix^pow(a)); operands are canonical (materialised at definition)
+    if (state[s.c] == ST_ZERO) {           // inner chain is empty: nothing is added
+      if (state[s.a] == ST_ZERO) state[id] = ST_ZERO;
+      else { o << "  const F4 m" << id << " = m" << s.a << ";\n"; state[id] = ST_CANON; }
+      continue;
+    }
+    o << "  const F4 m" << id << " = ";
+    if (state[s.a] == ST_ZERO) o << "scale4(mul4(m" << s.c << ", tof4(PW(" << mx_pow[s.a] << "))), f" << s.b << ")";
+    else o << "add4(m" << s.a << ", scale4(mul4(m" << s.c << ", tof4(PW(" << mx_pow[s.a] << "))), f" << s.b << "))";
+    o << ";\n";
+    state[id] = ST_CANON;
   }
   o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
-  if (mx_zero[c.ret]) o << "  F4 r; r.a = r.b = r.c = r.d = 0;\n";
+  if (state[c.ret] == ST_ZERO) o << "  F4 r; r.a = r.b = r.c = r.d = 0;\n";
   else o << "  const F4 r = scale4(m" << c.ret << ", den);\n";
   o << "  check[c] = r.a; check[dom + c] = r.b; check[2 * dom + c] = r.c; check[3 * dom + c] = r.d;\n}\n";
   return o.str();
@@ -218,7 +279,7 @@ static std::string cache_dir() {
   }
   return "/tmp/zkb200-cache";
 }
-static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 16 ? 16 : v; }
+static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : v > 16 ? 16 : v; }
 
 static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
   Api& a = api();
@@ -285,6 +346,10 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, std::s
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
   if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
   if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleLoadData: ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
+  if (const_mode(c, np)) {
+    r = a.moduleGetGlobal(&k.cdata, &k.cdata_bytes, k.mod, "zkb_cd");
+    if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleGetGlobal(zkb_cd): ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
+  }
   return &(cache->kernels[key] = k);
 }
 
@@ -303,8 +368,15 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   for (uint32_t i = 0; i < c.mix_size; ++i) gl[i] = mix_g[i];
   for (uint32_t i = 0; i < c.out_size; ++i) gl[c.mix_size + i] = out_g[i];
   uint32_t* d_data = nullptr;
-  ZKB_CUDA(cudaMallocAsync((void**)&d_data, h.size() * 4, ctx->stream));
-  ZKB_CUDA(cudaMemcpyAsync(d_data, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t data_words = 4 * (size_t)k->n_powers + c.mix_size + c.out_size;
+  if (k->cdata) {
+    ZKB_REQUIRE(data_words * 4 <= k->cdata_bytes, "eval_check JIT: constant bank smaller than the per-proof data");
+    CUresult cr = api().memcpyHtoDAsync(k->cdata, h.data(), data_words * 4, (CUstream)ctx->stream);    // pageable source: staged before the call returns
+    if (cr != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(cr, &s); throw Error(std::string("zkb200: eval_check JIT constant upload failed: ") + (s ? s : "?")); }
+  } else {
+    ZKB_CUDA(cudaMallocAsync((void**)&d_data, h.size() * 4, ctx->stream));
+    ZKB_CUDA(cudaMemcpyAsync(d_data, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
   Fp w4 = pow(Fp::from(137), (uint64_t)1 << (MAX_ROU_PO2 - 2));
   Fp three_n = pow(Fp::from(3), n);
   uint4 invden; uint32_t* idp = &invden.x;
@@ -317,7 +389,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   CUresult r = api().launchKernel(k->fn, (unsigned)(domain / JIT_BLOCK), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
-  ZKB_CUDA(cudaFreeAsync(d_data, ctx->stream));
+  if (d_data) ZKB_CUDA(cudaFreeAsync(d_data, ctx->stream));
   return true;
 }
 
