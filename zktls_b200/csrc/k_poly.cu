@@ -154,53 +154,70 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict_
 }
 
 // ---- batch_evaluate_any (DEEP) -------------------------------------------------------------------------
-// Slab kernel: block (slab, j) evaluates sum_{i in slab} coeffs[which[j]][i] * x^i.  Each warp sweeps a
-// contiguous run of its slab with coalesced loads; lane l accumulates sum_m c[32m + l] * (x^32)^m with 4 modmul
-// per coefficient, and the x^l / x^(warp base) / x^(slab base) factors are applied once at the end.
+// out[j] = sum_i coeffs[which[j]][i] * x_j^i with Fp coefficients and an Fp4 point.  Write i = slab * SLAB + m * 256 + t
+// (t = thread, m = step): thread t of block (slab, j) accumulates sum_m c[..] * (x^256)^m LAZILY -- one IMAD.WIDE per
+// coefficient and Fp4 component into a 64-bit accumulator whose high word is brought back below P after every second term
+// (see fixhi) -- and only then multiplies by x^t, reduces over the block and scales by x^(slab * SLAB).  All powers come
+// from per-point tables built by a small pre-kernel, so the main loop is 4 IMAD.WIDE + 2 fix-ups per coefficient
+// (the canonical form costs 4 Montgomery multiplications + 4 modular additions).
 constexpr int EVAL_THREADS = 256, EVAL_WARPS = EVAL_THREADS / 32, EVAL_STEPS = 64;
 constexpr size_t EVAL_SLAB = (size_t)EVAL_THREADS * EVAL_STEPS;     // 16384 coefficients
+// tables per evaluation point j: [x^t, t < 256][x^(256 m), m < 64][x^(slab * SLAB), slab < n_slabs]
+__host__ __device__ inline size_t eval_table_stride(uint32_t n_slabs) { return (size_t)EVAL_THREADS + EVAL_STEPS + n_slabs; }
+__global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restrict__ xs, uint32_t n_slabs, uint32_t n_eval) {
+  const size_t stride = eval_table_stride(n_slabs);
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= stride * n_eval) return;
+  uint32_t j = (uint32_t)(g / stride), e = (uint32_t)(g % stride);
+  uint4 xv = xs[j];
+  uint64_t exp = e < EVAL_THREADS ? e : e < EVAL_THREADS + EVAL_STEPS ? (uint64_t)(e - EVAL_THREADS) * EVAL_THREADS : (uint64_t)(e - EVAL_THREADS - EVAL_STEPS) * EVAL_SLAB;
+  Fp4 r = pow(ld4(xv), exp);
+  tables[g] = st4(r);
+}
+__device__ __forceinline__ uint64_t fixhi(uint64_t a) {       // high word < 2P  ->  high word < P (value mod P unchanged)
+  uint32_t hi = (uint32_t)(a >> 32);
+  uint32_t y = hi - P;
+  hi = y < hi ? y : hi;
+  return ((uint64_t)hi << 32) | (uint32_t)a;
+}
+__device__ __forceinline__ uint32_t fin_acc(uint64_t a) { return reduce_2p(mont_redc_lazy(fixhi(a))); }
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__ partial, const uint32_t* __restrict__ coeffs, size_t n,
-                                                              const uint32_t* __restrict__ which, const uint4* __restrict__ xs, uint32_t n_slabs) {
-  __shared__ uint4 s_x32[EVAL_STEPS];
+                                                              const uint32_t* __restrict__ which, const uint4* __restrict__ tables, uint32_t n_slabs) {
+  __shared__ uint4 s_pw[EVAL_STEPS];
   __shared__ uint4 s_red[EVAL_WARPS];
   const uint32_t slab = blockIdx.x, j = blockIdx.y;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint4 xv = xs[j];
-  const Fp4 x = ld4(xv);
-  if (threadIdx.x < EVAL_STEPS) {
-    Fp4 x32 = x;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) x32 *= x32;
-    Fp4 p = pow(x32, threadIdx.x);
-    s_x32[threadIdx.x] = st4(p);
-  }
+  const uint4* tab = tables + (size_t)j * eval_table_stride(n_slabs);
+  if (threadIdx.x < EVAL_STEPS) s_pw[threadIdx.x] = tab[EVAL_THREADS + threadIdx.x];
   __syncthreads();
   const uint32_t* col = coeffs + (size_t)which[j] * n;
-  size_t warp_base = (size_t)slab * EVAL_SLAB + (size_t)warp * (32 * EVAL_STEPS);
-  Fp4 acc;
-#pragma unroll 4
-  for (int m = 0; m < EVAL_STEPS; ++m) {
-    size_t i = warp_base + (size_t)m * 32 + lane;
-    uint32_t c = i < n ? __ldg(col + i) : 0u;
-    uint4 p = s_x32[m];
-    acc += ld4(p) * Fp(c);
+  const size_t base = (size_t)slab * EVAL_SLAB + threadIdx.x;
+  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 8
+  for (int m = 0; m < EVAL_STEPS; m += 2) {
+    size_t i0 = base + (size_t)m * EVAL_THREADS, i1 = i0 + EVAL_THREADS;
+    uint32_t c0 = i0 < n ? __ldg(col + i0) : 0u, c1 = i1 < n ? __ldg(col + i1) : 0u;
+    uint4 p0 = s_pw[m], p1 = s_pw[m + 1];
+    a0 += (uint64_t)c0 * p0.x; a1 += (uint64_t)c0 * p0.y; a2 += (uint64_t)c0 * p0.z; a3 += (uint64_t)c0 * p0.w;
+    a0 += (uint64_t)c1 * p1.x; a1 += (uint64_t)c1 * p1.y; a2 += (uint64_t)c1 * p1.z; a3 += (uint64_t)c1 * p1.w;
+    a0 = fixhi(a0); a1 = fixhi(a1); a2 = fixhi(a2); a3 = fixhi(a3);
   }
-  acc *= pow(x, lane);
-  // warp reduction
+  Fp4 acc = Fp4::raw(fin_acc(a0), fin_acc(a1), fin_acc(a2), fin_acc(a3));
+  uint4 xt = tab[threadIdx.x];
+  acc *= ld4(xt);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     Fp4 o = Fp4::raw(__shfl_down_sync(0xffffffffu, acc.c[0].v, off), __shfl_down_sync(0xffffffffu, acc.c[1].v, off),
                      __shfl_down_sync(0xffffffffu, acc.c[2].v, off), __shfl_down_sync(0xffffffffu, acc.c[3].v, off));
     acc += o;
   }
-  if (lane == 0) {
-    acc *= pow(x, (uint64_t)warp_base);
-    s_red[warp] = st4(acc);
-  }
+  if (lane == 0) s_red[warp] = st4(acc);
   __syncthreads();
   if (threadIdx.x == 0) {
     Fp4 t;
     for (int w = 0; w < EVAL_WARPS; ++w) { uint4 v = s_red[w]; t += ld4(v); }
+    uint4 xs = tab[EVAL_THREADS + EVAL_STEPS + slab];
+    t *= ld4(xs);
     partial[(size_t)j * n_slabs + slab] = st4(t);
   }
 }
@@ -367,11 +384,14 @@ void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uin
   if (!n_eval) return;
   size_t n = (size_t)1 << po2;
   uint32_t n_slabs = (uint32_t)((n + EVAL_SLAB - 1) / EVAL_SLAB);
-  uint4* partial = (uint4*)scratch(ctx, n_eval * n_slabs * 16);
+  const size_t stride = eval_table_stride(n_slabs);
+  uint4* partial = (uint4*)scratch(ctx, (n_eval * n_slabs + n_eval * stride) * 16);
+  uint4* tables = partial + n_eval * n_slabs;
+  k_eval_tables<<<grid_for(stride * n_eval, 128), 128, 0, ctx->stream>>>(tables, (const uint4*)d_xs, n_slabs, (uint32_t)n_eval); launched(ctx);
   for (size_t j0 = 0; j0 < n_eval; j0 += 32768) {      // grid.y limit
     uint32_t nj = (uint32_t)std::min<size_t>(32768, n_eval - j0);
     dim3 grid(n_slabs, nj);
-    k_eval_slabs<<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, (const uint4*)d_xs + j0, n_slabs); launched(ctx);
+    k_eval_slabs<<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs); launched(ctx);
   }
   k_eval_reduce<<<grid_for(n_eval, 128), 128, 0, ctx->stream>>>((uint4*)d_out, partial, n_slabs, (uint32_t)n_eval); launched(ctx);
 }
