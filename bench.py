@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
     ap.add_argument("--cpu-sample-po2", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, help="segments proven concurrently per GPU (one host thread + stream each)")
     ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -183,8 +184,13 @@ def main():
     n = 1 << po2
     shape = circuit.SYN280
     blob = circuit.syn_circuit(**shape).blob()
-    hal = B200Hal(local_rank)
-    prover = SegmentProver(hal, blob)
+    # `inflight` segments are proven concurrently per GPU, each by its own host thread + ctx (stream) + prover: one segment's
+    # latency-bound stretches (Merkle tree tops, FRI rounds, Fiat-Shamir round trips) are filled by the other's kernels
+    # (">= 2 segments in flight per GPU").  A ctx is used by one thread at a time, as the C-ABI requires.
+    inflight = max(1, args.inflight)
+    hals = [B200Hal(local_rank) for _ in range(inflight)]
+    provers = [SegmentProver(h, blob) for h in hals]
+    hal, prover = hals[0], provers[0]
 
     # synthetic trace, generated on the device (uniform field elements), seeded per rank
     g = torch.Generator(device=dev); g.manual_seed(0xB2000000 + rank)
@@ -193,42 +199,66 @@ def main():
     d_code, d_data, d_accum = rand_fp(shape["code_cols"] * n), rand_fp(shape["data_cols"] * n), rand_fp(shape["accum_cols"] * n)
     io = np.random.default_rng(rank).integers(0, P, size=shape["out_size"], dtype=np.uint32)
     from zktls_b200.hal import Buffer
-    as_buf = lambda t: Buffer(hal, t.data_ptr(), t.numel(), 1, owner=t)
-    b_code, b_data, b_accum = as_buf(d_code), as_buf(d_data), as_buf(d_accum)
+    bufs = [[Buffer(h, t.data_ptr(), t.numel(), 1, owner=t) for t in (d_code, d_data, d_accum)] for h in hals]
     # pinned host copies for the end-to-end arm
     h_code, h_data, h_accum = (t.cpu().pin_memory() for t in (d_code, d_data, d_accum))
     h_np = [t.numpy().view(np.uint32) for t in (h_code, h_data, h_accum)]
     trace_bytes = sum(t.numel() * 4 for t in (d_code, d_data, d_accum))
     torch.cuda.synchronize()
 
-    def step_device():
-        return prover.prove(po2, io, b_code, b_data, b_accum)
+    def run_workers(fn, k):
+        """segments 0..k-1 over the `inflight` workers (worker w takes w, w + inflight, ...); returns the last seal of worker 0"""
+        out, errs = [None] * inflight, []
+        def work(w):
+            try:
+                out[w] = fn(w, len(range(w, k, inflight)))
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(w,)) for w in range(1, inflight)]
+        for th in ths: th.start()
+        work(0)
+        for th in ths: th.join()
+        if errs:
+            raise errs[0]
+        return out[0]
 
-    def steps_host(k):
+    def device_worker(w, k):
+        s = None
+        for _ in range(k):
+            s = provers[w].prove(po2, io, *bufs[w])
+        return s
+
+    def host_worker(w, k):
         """k segments from HOST (pinned) buffers through the C-ABI, double-buffered: the 1.17 GB upload of segment i+1 runs on
         the copy stream while segment i is proven (what a session's queue of continuation segments does).  Every segment's
         host->device copy and seal read-back happen inside this call."""
-        prover.stage(po2, h_np[0], h_np[1], h_np[2])
+        s = None
+        if k:
+            # the workers' FIRST uploads take turns on the PCIe link (worker w starts when worker w-1's has landed); after
+            # that every upload hides behind a proof
+            if w > 0:
+                first_up[w - 1].wait()
+            provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
+            provers[w].stage_wait()
+        first_up[w].set()
         for i in range(k):
             if i + 1 < k:
-                prover.stage(po2, h_np[0], h_np[1], h_np[2])
-            s = prover.prove_staged(io)
+                provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
+            s = provers[w].prove_staged(io)
         return s
 
     # ---- device-resident arm -----------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank); sampler.start()
-    for _ in range(args.warmup):
-        seal = step_device()
+    seal = run_workers(device_worker, args.warmup * inflight)          # every worker warms up `warmup` times
     barrier()
-    l0 = hal.kernel_launches()
-    hal.timer_start(); t0 = time.time()
-    for _ in range(args.steps):
-        seal = step_device()
+    l0 = sum(h.kernel_launches() for h in hals)
+    hal.timer_start(); t0 = time.time()           # event on worker 0's stream; every prove call returns with its seal on the host,
+    seal = run_workers(device_worker, args.steps)  # so when the workers have joined all device work of the K steps is complete
     ms_dev = hal.timer_stop()
     barrier()
     t1 = time.time()
     wall = t1 - t0
-    launches = hal.kernel_launches() - l0
+    launches = sum(h.kernel_launches() for h in hals) - l0
     clocks = sampler.stop(t0, t1)
     t = torch.tensor([ms_dev], device=dev, dtype=torch.float64)
     if world > 1:
@@ -238,10 +268,12 @@ def main():
     value = world * args.steps / (ms_total / 1000.0)
 
     # ---- end-to-end arm: host buffers through the C-ABI prove call ------------------------------------------------------
-    seal_h = steps_host(min(args.warmup, 2))
+    first_up = [threading.Event() for _ in range(inflight)]
+    seal_h = run_workers(host_worker, min(args.warmup, 2) * inflight)
     barrier()
+    first_up = [threading.Event() for _ in range(inflight)]
     hal.timer_start()
-    seal_h = steps_host(args.steps)
+    seal_h = run_workers(host_worker, args.steps)
     ms_e2e = hal.timer_stop()
     barrier()
     t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
@@ -302,14 +334,15 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
-                "config": workload_config(), "clocks": clocks,
+                "config": dict(workload_config(), segments_in_flight_per_gpu=inflight), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if po2 != PO2:
             line["config"]["workload"] = f"DEBUG po2={po2} (not the benchmark config)"
         print(json.dumps(line), flush=True)
-    prover.close()
+    for pr in provers:
+        pr.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -151,6 +151,9 @@ zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const vo
  * Staging segment k+1 before proving segment k overlaps its upload with the proof.  At most two segments may be staged. */
 zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, const void* h_data, const void* h_accum);
 zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io);
+/* Blocks until every upload started by zkb_prover_stage_traces on this prover has landed (lets several provers that share
+ * one PCIe link take turns instead of splitting its bandwidth). */
+zkb_err zkb_prover_stage_wait(zkb_prover* p);
 /* CPU verifier for a seal produced by the prover (risc0-zkp verify/*): checks the transcript, Merkle paths, FRI
  * and the constraint relation at the DEEP point.  Host-only, like the reference's verifier. */
 zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words);

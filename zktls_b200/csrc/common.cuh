@@ -51,6 +51,8 @@ struct zkb_ctx {
   void* staging = nullptr;                // pinned host staging for small parameter uploads
   size_t staging_bytes = 0;
   void* jit = nullptr;                    // EvalJitCache* (k_eval_jit.cu): per-circuit NVRTC-compiled eval_check kernels
+  cudaMemPool_t pool = nullptr;           // this ctx's own stream-ordered pool: several ctxs proving concurrently on one GPU never
+                                          // wait on (or steal) each other's freed blocks; release threshold = never
 };
 
 namespace zkb {
@@ -72,6 +74,11 @@ inline void* scratch(zkb_ctx* ctx, size_t bytes) {
   }
   return ctx->scratch;
 }
+// stream-ordered temporary from the ctx's own pool (freed with pool_free on the same stream)
+template <typename T> inline void pool_alloc(zkb_ctx* ctx, T** out, size_t bytes) {
+  ZKB_CUDA(cudaMallocFromPoolAsync((void**)out, bytes < 16 ? 16 : bytes, ctx->pool, ctx->stream));
+}
+inline void pool_free(zkb_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 inline unsigned grid_for(size_t work, unsigned block) { return (unsigned)((work + block - 1) / block); }
 

@@ -27,6 +27,16 @@ static zkb_err init_common(int device, cudaStream_t borrowed, bool borrow, zkb_c
   ctx->sm_count = prop.multiProcessorCount;
   if (borrow) { ctx->stream = borrowed; ctx->owns_stream = false; }
   else { ZKB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->owns_stream = true; }
+  {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    ZKB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+    uint64_t threshold = UINT64_MAX;      // keep freed blocks: a segment re-uses the same ~8 GB every time
+    ZKB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  }
   ZKB_CUDA(cudaEventCreate(&ctx->ev0));
   ZKB_CUDA(cudaEventCreate(&ctx->ev1));
   ctx->staging_bytes = 1u << 20;
@@ -48,6 +58,7 @@ zkb_err zkb_destroy(zkb_ctx* ctx) {
   if (ctx->staging) cudaFreeHost(ctx->staging);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   ZKB_API_END

@@ -199,8 +199,8 @@ void eval_check(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint
   for (uint32_t i = 0; i < std::max<uint32_t>(prog.n_powers, 1); ++i) { cur.store(&pw[4 * i]); cur *= poly_mix; }
   uint4 *d_code = nullptr, *d_pw = nullptr;
   size_t code_bytes = std::max<size_t>(prog.code.size(), 1) * 16;
-  ZKB_CUDA(cudaMallocAsync((void**)&d_code, code_bytes, ctx->stream));
-  ZKB_CUDA(cudaMallocAsync((void**)&d_pw, pw.size() * 4, ctx->stream));
+  pool_alloc(ctx, &d_code, code_bytes);
+  pool_alloc(ctx, &d_pw, pw.size() * 4);
   if (!prog.code.empty()) ZKB_CUDA(cudaMemcpyAsync(d_code, prog.code.data(), prog.code.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
   ZKB_CUDA(cudaMemcpyAsync(d_pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   EvalArgs args;
@@ -219,8 +219,8 @@ void eval_check(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(k_eval_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_eval_check<<<(unsigned)(domain / block), block, smem, ctx->stream>>>(d_check, d_code, d_pw, args);
   launched(ctx);
-  ZKB_CUDA(cudaFreeAsync(d_code, ctx->stream));
-  ZKB_CUDA(cudaFreeAsync(d_pw, ctx->stream));
+  pool_free(ctx, d_code);
+  pool_free(ctx, d_pw);
 }
 
 }  // namespace zkb

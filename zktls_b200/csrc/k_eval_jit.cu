@@ -374,7 +374,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
     CUresult cr = api().memcpyHtoDAsync(k->cdata, h.data(), data_words * 4, (CUstream)ctx->stream);    // pageable source: staged before the call returns
     if (cr != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(cr, &s); throw Error(std::string("zkb200: eval_check JIT constant upload failed: ") + (s ? s : "?")); }
   } else {
-    ZKB_CUDA(cudaMallocAsync((void**)&d_data, h.size() * 4, ctx->stream));
+    pool_alloc(ctx, &d_data, h.size() * 4);
     ZKB_CUDA(cudaMemcpyAsync(d_data, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   Fp w4 = pow(Fp::from(137), (uint64_t)1 << (MAX_ROU_PO2 - 2));
@@ -389,7 +389,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   CUresult r = api().launchKernel(k->fn, (unsigned)(domain / JIT_BLOCK), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
-  if (d_data) ZKB_CUDA(cudaFreeAsync(d_data, ctx->stream));
+  if (d_data) pool_free(ctx, d_data);
   return true;
 }
 

@@ -403,11 +403,11 @@ void poly_divide(zkb_ctx* ctx, uint32_t* d_poly, size_t n, const Fp4& z, uint32_
   }
   size_t chunks = (n + DIV_CHUNK - 1) / DIV_CHUNK;
   uint4* totals = nullptr;
-  ZKB_CUDA(cudaMallocAsync((void**)&totals, chunks * 16, ctx->stream));
+  pool_alloc(ctx, &totals, chunks * 16);
   k_div_totals<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>(totals, (const uint4*)d_poly, n, to_arg(z)); launched(ctx);
   poly_divide(ctx, (uint32_t*)totals, chunks, pow(z, DIV_CHUNK), d_rem);
   k_div_apply<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>((uint4*)d_poly, totals, n, to_arg(z)); launched(ctx);
-  ZKB_CUDA(cudaFreeAsync(totals, ctx->stream));
+  pool_free(ctx, totals);
 }
 void prefix_products(zkb_ctx* ctx, uint32_t* d_io, size_t n) {
   if (n <= 4 * PP_CHUNK) {
@@ -416,11 +416,11 @@ void prefix_products(zkb_ctx* ctx, uint32_t* d_io, size_t n) {
   }
   size_t chunks = (n + PP_CHUNK - 1) / PP_CHUNK;
   uint4* totals = nullptr;
-  ZKB_CUDA(cudaMallocAsync((void**)&totals, chunks * 16, ctx->stream));
+  pool_alloc(ctx, &totals, chunks * 16);
   k_pp_totals<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>(totals, (const uint4*)d_io, n); launched(ctx);
   prefix_products(ctx, (uint32_t*)totals, chunks);
   k_pp_apply<<<grid_for(chunks, 128), 128, 0, ctx->stream>>>((uint4*)d_io, totals, n); launched(ctx);
-  ZKB_CUDA(cudaFreeAsync(totals, ctx->stream));
+  pool_free(ctx, totals);
 }
 
 }  // namespace zkb

@@ -28,7 +28,7 @@ struct WriteIOP {
 struct DevBuf {
   zkb_ctx* ctx = nullptr; uint32_t* p = nullptr; size_t words = 0;
   DevBuf() {}
-  DevBuf(zkb_ctx* c, size_t w) : ctx(c), words(w) { ZKB_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(w, 4) * 4, c->stream)); }
+  DevBuf(zkb_ctx* c, size_t w) : ctx(c), words(w) { pool_alloc(c, &p, std::max<size_t>(w, 4) * 4); }
   DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
   DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
   DevBuf& operator=(DevBuf&& o) noexcept { reset(); ctx = o.ctx; p = o.p; words = o.words; o.p = nullptr; o.words = 0; return *this; }
@@ -443,11 +443,6 @@ zkb_err zkb_prover_new(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_w
   p->ctx = ctx;
   p->circuit = CircuitDef::parse(h_circuit, circuit_words);
   p->reset();
-  // keep freed blocks in the stream-ordered pool: a segment re-uses the same ~8 GB every time
-  cudaMemPool_t pool;
-  ZKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-  uint64_t threshold = UINT64_MAX;
-  ZKB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   *out = p.release();
   ZKB_API_END
 }
@@ -488,6 +483,13 @@ zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, cons
   tr[GROUP_ACCUM] = h_accum; tr[GROUP_CODE] = h_code; tr[GROUP_DATA] = h_data;
   for (int g = 0; g < 3; ++g) ZKB_REQUIRE(tr[g] || p->circuit.group_size[g] == 0, "null trace");
   p->stage_traces(po2, tr);
+  ZKB_API_END
+}
+zkb_err zkb_prover_stage_wait(zkb_prover* p) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(p != nullptr, "null prover");
+  use(p->ctx);
+  if (p->copy_stream) ZKB_CUDA(cudaStreamSynchronize(p->copy_stream));
   ZKB_API_END
 }
 zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io) {

@@ -62,6 +62,9 @@ class SegmentProver:
         self._staged = getattr(self, "_staged", []) + [arrs]
         check(lib().zkb_prover_stage_traces(self.h, C.c_int(po2), *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
 
+    def stage_wait(self):
+        check(lib().zkb_prover_stage_wait(self.h))
+
     def prove_staged(self, io):
         io = np.ascontiguousarray(io, dtype=np.uint32)
         check(lib().zkb_prove_staged(self.h, _hp(io)))
