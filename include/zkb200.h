@@ -110,6 +110,11 @@ zkb_err zkb_eltwise_copy_elem(zkb_ctx* ctx, void* d_out, const void* d_in, size_
 zkb_err zkb_eltwise_zeroize_elem(zkb_ctx* ctx, void* d_io, size_t n);
 zkb_err zkb_gather_sample(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t idx, size_t size, size_t stride);
 zkb_err zkb_prefix_products(zkb_ctx* ctx, void* d_io_fp4, size_t n);
+/* Hal::scatter(into, index, offsets, values) (witness-generation helper): for every row r < n_rows and k in
+ * [h_index[r], h_index[r+1]): into[h_offsets[k]] = h_values[k].  index/offsets/values are host slices as in the trait;
+ * an offset >= into_len is an error. */
+zkb_err zkb_scatter(zkb_ctx* ctx, void* d_into, size_t into_len, const uint32_t* h_index, size_t n_rows, const uint32_t* h_offsets,
+                    const uint32_t* h_values);
 
 /* ---- CircuitHal::eval_check ------------------------------------------------------------------------------- */
 /* check[j*4n + c] = (poly_fp(c) / ((3 w^c)^n - 1))[j] over the LDE domain (4n points).  The constraint system is

@@ -150,6 +150,11 @@ static void eltwise_copy_elem(Fp* o, const Fp* a, size_t n) { for (size_t i = 0;
 static void eltwise_zeroize_elem(Fp* x, size_t n) { for (size_t i = 0; i < n; ++i) if (x[i].v == INVALID) x[i].v = 0; }
 static void gather_sample(Fp* dst, const Fp* src, size_t idx, size_t size, size_t stride) { for (size_t i = 0; i < size; ++i) dst[i] = src[idx + i * stride]; }
 static void prefix_products(Fp4* io, size_t n) { for (size_t i = 1; i < n; ++i) io[i] *= io[i - 1]; }
+// Hal::scatter(into, index, offsets, values) (witgen helper, App. C): row r owns entries index[r] .. index[r+1]
+static void scatter(Fp* into, const uint32_t* index, size_t n_rows, const uint32_t* offsets, const Fp* values) {
+  for (size_t r = 0; r < n_rows; ++r)
+    for (uint32_t k = index[r]; k < index[r + 1]; ++k) into[offsets[k]] = values[k];
+}
 
 // ---- core::poly -----------------------------------------------------------------------------------
 static Fp4 poly_eval(const Fp4* coeffs, size_t n, Fp4 x) {

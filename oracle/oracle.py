@@ -198,6 +198,11 @@ def gather_sample(src, idx, size, stride):
     out = np.zeros(size, np.uint32); lib().orc_gather_sample(_p(out), _p(u32(src)), _sz(idx), _sz(size), _sz(stride)); return out
 
 
+def scatter(into, index, offsets, values):
+    into = u32(into).copy(); index = u32(index)
+    lib().orc_scatter(_p(into), _p(index), _sz(index.size - 1), _p(u32(offsets)), _p(u32(values))); return into
+
+
 def prefix_products(io):
     io = u32(io).copy(); lib().orc_prefix_products(_p(io), _sz(io.size // 4)); return io
 

@@ -73,6 +73,7 @@ void orc_eltwise_copy_elem(uint32_t* o, const uint32_t* a, size_t n) { eltwise_c
 void orc_eltwise_zeroize_elem(uint32_t* x, size_t n) { eltwise_zeroize_elem((Fp*)x, n); }
 void orc_gather_sample(uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) { gather_sample((Fp*)dst, (const Fp*)src, idx, size, stride); }
 void orc_prefix_products(uint32_t* io, size_t n) { prefix_products((Fp4*)io, n); }
+void orc_scatter(uint32_t* into, const uint32_t* index, size_t n_rows, const uint32_t* offsets, const uint32_t* values) { scatter((Fp*)into, index, n_rows, offsets, (const Fp*)values); }
 // returns the remainder in rem[4]
 void orc_poly_divide(uint32_t* p, size_t n, const uint32_t* z, uint32_t* rem) { Fp4 r = poly_divide((Fp4*)p, n, ld4(z)); memcpy(rem, &r, 16); }
 void orc_poly_interpolate(uint32_t* out, const uint32_t* x, const uint32_t* fx, size_t size) { poly_interpolate((Fp4*)out, (const Fp4*)x, (const Fp4*)fx, size); }

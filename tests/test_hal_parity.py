@@ -246,3 +246,22 @@ def test_ntt_many_columns_crosses_l2_batches(hal, oracle):
     hal.batch_interpolate_ntt_zk_shift(b, count)
     want = oracle.zk_shift(oracle.batch_interpolate_ntt(x, count, po2), count, po2)
     assert np.array_equal(b.to_numpy(), want)
+
+
+@pytest.mark.parametrize("rows,per_row", [(1, 1), (7, 3), (1000, 5)])
+def test_scatter(hal, oracle, rows, per_row):
+    rng = np.random.default_rng(rows)
+    counts = rng.integers(0, per_row + 1, size=rows)
+    index = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    total = int(index[-1]); size = max(2 * total, 8)
+    offsets = rng.permutation(size)[:total].astype(np.uint32)        # distinct targets: order-independent result
+    values = oracle.random_fp(rng, total)
+    into0 = oracle.random_fp(rng, size)
+    buf = hal.copy_from_elem(into0)
+    hal.scatter(buf, index, offsets, values)
+    assert np.array_equal(buf.to_numpy(), oracle.scatter(into0, index, offsets, values))
+    if total:
+        from zktls_b200 import ZkbError
+        bad = offsets.copy(); bad[0] = size
+        with pytest.raises(ZkbError, match="outside"):
+            hal.scatter(buf, index, bad, values)

@@ -38,8 +38,16 @@ __host__ __device__ constexpr int rev4(int r) { return ((r & 1) << 3) | ((r & 2)
 // One round of butterfly levels on the 16 registers.  The registers are the values of local-index bits [p, p+4);
 // levels JLO <= j < JHI (absolute bit q = p + j) are processed: descending for the DIF (inverse), ascending for the
 // DIT (forward).  `lo` = the thread's local-index bits below p.  twl = per-level twiddle table for this direction.
+// x * w mod P in [0, 2P) for ANY 32-bit x, w a plain (non-Montgomery) constant with its Shoup quotient wq = floor(w 2^32 / P):
+// one IMAD.HI + two IMAD (the Montgomery form needs IMAD.WIDE + IMAD + IMAD.HI and a canonical-range operand).
+__device__ __forceinline__ uint32_t shoup_lazy(uint32_t x, uint2 w) { return x * w.x - __umulhi(x, w.y) * P; }
+
+// Values stay LAZY, in [0, 2P), between butterfly levels: each butterfly brings its two inputs below P (one VIADDMNMX
+// each), then a' = a + t and b' = a - t + P are again below 2P with no further correction -- 4 ALU + 3 multiplier-pipe
+// instructions per butterfly instead of 6 + 3.  Callers reduce once before storing (or multiply by a canonical
+// Montgomery word, which accepts a lazy operand).
 template <bool INV, int JLO, int JHI>
-__device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, const uint32_t lo, const uint32_t* __restrict__ twl) {
+__device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, const uint32_t lo, const uint2* __restrict__ twl) {
   if (INV) {
 #pragma unroll
     for (int j = JHI - 1; j >= JLO; --j) {
@@ -47,11 +55,11 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         if (r & (1 << j)) continue;
-        uint32_t a = v[r], b = v[r | (1 << j)];
-        v[r] = add_mod(a, b);
-        uint32_t d = sub_mod(a, b);
+        uint32_t a = reduce_2p(v[r]), b = reduce_2p(v[r | (1 << j)]);
+        v[r] = a + b;
+        uint32_t d = a - b + P;
         if (q == 0) v[r | (1 << j)] = d;
-        else v[r | (1 << j)] = mont_mul(d, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
+        else v[r | (1 << j)] = shoup_lazy(d, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
       }
     }
   } else {
@@ -61,13 +69,18 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         if (r & (1 << j)) continue;
-        uint32_t a = v[r], b = v[r | (1 << j)];
-        if (q != 0) b = mont_mul(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
-        v[r] = add_mod(a, b);
-        v[r | (1 << j)] = sub_mod(a, b);
+        uint32_t a = reduce_2p(v[r]), b = v[r | (1 << j)];
+        if (q != 0) b = shoup_lazy(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
+        b = reduce_2p(b);
+        v[r] = a + b;
+        v[r | (1 << j)] = a - b + P;
       }
     }
   }
+}
+template <int N> __device__ __forceinline__ void canonicalize(uint32_t (&v)[N]) {
+#pragma unroll
+  for (int r = 0; r < N; ++r) v[r] = reduce_2p(v[r]);
 }
 
 // local index of register r for thread t in a round whose register field starts at bit p
@@ -81,7 +94,7 @@ enum : int { EPI_NONE = 0, EPI_SCALE = 1, EPI_TABLE = 2 };
 
 // Inverse: in place.  epilogue multiplies position x of every 2^A block by table[x] (EPI_TABLE) or by `scale`.
 template <int A, int EPI>
-__global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, const uint32_t* __restrict__ table, uint32_t scale) {
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ io, const uint2* __restrict__ twl, const uint32_t* __restrict__ table, uint32_t scale) {
   __shared__ uint32_t sm[phys_size(TILE)];
   constexpr int L = 1 << A, TPB = L / 16;           // threads per sub-transform
   const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
@@ -122,6 +135,8 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
   } else if (EPI == EPI_SCALE) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = mont_mul(v[r], scale);
+  } else {
+    canonicalize(v);
   }
 #pragma unroll
   for (int g = 0; g < 4; ++g) reinterpret_cast<uint4*>(o)[g] = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 // Forward: out-of-place capable; EB = expand bits (0 or 2): out block element x <- in[(block_base + x) >> EB], and the
 // lowest EB levels are skipped.
 template <int A, int EB>
-__global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint32_t* __restrict__ twl) {
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint2* __restrict__ twl) {
   __shared__ uint32_t sm[phys_size(TILE)];
   constexpr int L = 1 << A, TPB = L / 16;
   const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
@@ -165,6 +180,7 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ 
     p_prev = pc;
   }
   // p_prev == A - 4: register r is element r * TPB + t
+  canonicalize(v);
   uint32_t* o = out + gbase;
 #pragma unroll
   for (int r = 0; r < 16; ++r) o[(uint32_t)r * TPB + t] = v[r];
@@ -186,7 +202,7 @@ template <int A, int TL = 0> struct STile {
 };
 
 template <int A, bool INV, int TL = 0>
-__global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint32_t* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args) {
+__global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint2* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args) {
   constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
   extern __shared__ uint32_t sm[];
   const uint32_t tid = threadIdx.x;
@@ -261,28 +277,36 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
       else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
       p_prev = pc;
     }
+    canonicalize(v);
 #pragma unroll
     for (int r = 0; r < 16; ++r) base[((size_t)r * TPB + t) * S] = v[r];
   }
 }
 
 // ---- host side: tables, plans, launches ---------------------------------------------------------------------------
-static const uint32_t* level_table(zkb_ctx* ctx, bool inverse) {
+static const uint2* level_table(zkb_ctx* ctx, bool inverse) {
   NttTables* t = ntt_tables(ctx);
   int key = inverse ? 1 : 0;
   auto it = t->level_tables.find(key);
-  if (it != t->level_tables.end()) return it->second;
-  std::vector<uint32_t> h((size_t)1 << MAX_LEVEL_LOG, R_MOD_P);
+  if (it != t->level_tables.end()) return (const uint2*)it->second;
+  // entry (1 << q) + x = w_{2^(q+1)}^(+-x) as a PLAIN integer with its Shoup quotient floor(w 2^32 / P)
+  std::vector<uint32_t> h((size_t)2 << MAX_LEVEL_LOG, 0);
+  h[0] = 1; h[1] = (uint32_t)(((uint64_t)1 << 32) / P);
   for (int q = 0; q < MAX_LEVEL_LOG; ++q) {
     Fp w = inverse ? t->rou_rev[q + 1] : t->rou_fwd[q + 1];
     Fp cur = Fp::one();
-    for (uint32_t x = 0; x < (1u << q); ++x) { h[(1u << q) + x] = cur.v; cur *= w; }
+    for (uint32_t x = 0; x < (1u << q); ++x) {
+      uint32_t plain = cur.as_u32();
+      h[2 * ((1u << q) + x)] = plain;
+      h[2 * ((1u << q) + x) + 1] = (uint32_t)(((uint64_t)plain << 32) / P);
+      cur *= w;
+    }
   }
   uint32_t* d = nullptr;
   ZKB_CUDA(cudaMalloc((void**)&d, h.size() * 4));
   ZKB_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   t->level_tables[key] = d;
-  return d;
+  return (const uint2*)d;
 }
 // table[x] = mult * base^(rev_bits(x)) for x < 2^bits
 static const uint32_t* shift_table(zkb_ctx* ctx, int bits, Fp base, Fp mult) {
@@ -316,7 +340,7 @@ static bool make_plan(int k, Plan& pl) {
 }
 
 template <int A, bool INV, int TL = 0>
-static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
+static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
   using ST = STile<A, TL>;
   SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
   size_t tile_elems = (size_t)(1 << A) * ST::T;
@@ -328,7 +352,7 @@ static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, 
 }
 static int s_tile_log() { static int v = [] { const char* e = getenv("ZKB_NTT_S_TLOG"); return e ? atoi(e) : 3; }(); return v; }
 template <bool INV>
-static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint32_t* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
+static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g) {
   switch (a) {
     case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
     case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g); break;
@@ -349,7 +373,7 @@ static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_lo
   }
 }
 template <int EPI>
-static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, const uint32_t* twl, const uint32_t* table, uint32_t scale) {
+static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, const uint2* twl, const uint32_t* table, uint32_t scale) {
   unsigned grid = (unsigned)(total / TILE);
 #define ZKB_CI(AA) case AA: k_ntt_c_inv<AA, EPI><<<grid, C_THREADS, 0, ctx->stream>>>(io, twl, table, scale); break;
   switch (a) { ZKB_CI(4) ZKB_CI(5) ZKB_CI(6) ZKB_CI(7) ZKB_CI(8) ZKB_CI(9) ZKB_CI(10) ZKB_CI(11) ZKB_CI(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
@@ -357,7 +381,7 @@ static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, cons
   launched(ctx);
 }
 template <int EB>
-static void dispatch_c_fwd(zkb_ctx* ctx, int a, uint32_t* out, const uint32_t* in, size_t total, const uint32_t* twl) {
+static void dispatch_c_fwd(zkb_ctx* ctx, int a, uint32_t* out, const uint32_t* in, size_t total, const uint2* twl) {
   unsigned grid = (unsigned)(total / TILE);
 #define ZKB_CF(AA) case AA: k_ntt_c_fwd<AA, EB><<<grid, C_THREADS, 0, ctx->stream>>>(out, in, twl); break;
   switch (a) { ZKB_CF(4) ZKB_CF(5) ZKB_CF(6) ZKB_CF(7) ZKB_CF(8) ZKB_CF(9) ZKB_CF(10) ZKB_CF(11) ZKB_CF(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
@@ -388,7 +412,7 @@ bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shi
   if ((count * n) % TILE != 0) return false;          // tiny batches of tiny columns: level path
   NttTables* t = ntt_tables(ctx);
   TwiddleRef tw{t->d_hi, t->d_lo};
-  const uint32_t* twl = level_table(ctx, true);
+  const uint2* twl = level_table(ctx, true);
   const Fp scale = inv(Fp::from((uint32_t)1 << k));
   const Fp three = Fp::from(3);
   // per-pass parameters
@@ -432,7 +456,7 @@ bool ntt_forward_tiled(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t c
   if ((count * n) % TILE != 0) return false;
   NttTables* t = ntt_tables(ctx);
   TwiddleRef tw{t->d_hi, t->d_lo};
-  const uint32_t* twl = level_table(ctx, false);
+  const uint2* twl = level_table(ctx, false);
   size_t n_in = n >> expand_bits;
   size_t bc = batch_columns(count, (n + (out == in ? 0 : n_in)) * 4);
   for (size_t c0 = 0; c0 < count; c0 += bc) {

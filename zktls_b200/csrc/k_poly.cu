@@ -33,6 +33,13 @@ __global__ void k_gather(uint32_t* __restrict__ dst, const uint32_t* __restrict_
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < size) dst[i] = src[idx + i * stride];
 }
+// Hal::scatter: into[offsets[k]] = values[k] for k in [k0, k1)
+__global__ void k_scatter(uint32_t* __restrict__ into, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ values, size_t count, size_t into_len, uint32_t* __restrict__ bad) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  uint32_t o = offsets[k];
+  if (o < into_len) into[o] = values[k]; else atomicAdd(bad, 1u);
+}
 __global__ void k_expand(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, size_t total_out, int expand_bits) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total_out) out[i] = in[i >> expand_bits];     // columns are contiguous, so this holds across the batch
@@ -447,6 +454,28 @@ zkb_err zkb_eltwise_zeroize_elem(zkb_ctx* ctx, void* d_io, size_t n) {
 }
 zkb_err zkb_gather_sample(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t idx, size_t size, size_t stride) {
   ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_dst && d_src) || !size, "null buffer"); gather_sample(ctx, (uint32_t*)d_dst, (const uint32_t*)d_src, idx, size, stride); ZKB_API_END
+}
+zkb_err zkb_scatter(zkb_ctx* ctx, void* d_into, size_t into_len, const uint32_t* h_index, size_t n_rows, const uint32_t* h_offsets, const uint32_t* h_values) {
+  ZKB_API_BEGIN use(ctx);
+  ZKB_REQUIRE(h_index || !n_rows, "null index");
+  if (!n_rows) return nullptr;
+  const uint32_t k0 = h_index[0], k1 = h_index[n_rows];
+  for (size_t r = 0; r < n_rows; ++r) ZKB_REQUIRE(h_index[r] <= h_index[r + 1], "scatter: index must be non-decreasing");
+  if (k1 == k0) return nullptr;
+  ZKB_REQUIRE(d_into && h_offsets && h_values, "null buffer");
+  const size_t count = k1 - k0;
+  uint32_t* d_tmp = nullptr;
+  pool_alloc(ctx, &d_tmp, (2 * count + 1) * 4);
+  ZKB_CUDA(cudaMemcpyAsync(d_tmp, h_offsets + k0, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_CUDA(cudaMemcpyAsync(d_tmp + count, h_values + k0, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_CUDA(cudaMemsetAsync(d_tmp + 2 * count, 0, 4, ctx->stream));
+  k_scatter<<<grid_for(count, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>((uint32_t*)d_into, d_tmp, d_tmp + count, count, into_len, d_tmp + 2 * count); launched(ctx);
+  uint32_t bad = 0;
+  ZKB_CUDA(cudaMemcpyAsync(&bad, d_tmp + 2 * count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  pool_free(ctx, d_tmp);
+  ZKB_REQUIRE(bad == 0, "scatter: offset outside the destination buffer");
+  ZKB_API_END
 }
 zkb_err zkb_prefix_products(zkb_ctx* ctx, void* d_io_fp4, size_t n) {
   ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_io_fp4 && aligned16(d_io_fp4)) || !n, "null or misaligned buffer"); prefix_products(ctx, (uint32_t*)d_io_fp4, n); ZKB_API_END

@@ -200,6 +200,10 @@ class B200Hal:
     def prefix_products(self, io):
         check(lib().zkb_prefix_products(self.ctx, C.c_void_p(io.ptr), _sz(io.size)))
 
+    def scatter(self, into, index, offsets, values):
+        ix = np.ascontiguousarray(index, np.uint32); of = np.ascontiguousarray(offsets, np.uint32); va = np.ascontiguousarray(values, np.uint32)
+        check(lib().zkb_scatter(self.ctx, C.c_void_p(into.ptr), _sz(into.size), _hp(ix), _sz(max(ix.size - 1, 0)), _hp(of), _hp(va)))
+
     # ---- CircuitHal ---------------------------------------------------------------------------------------------
     def eval_check(self, check_buf, circuit_blob, accum, code, data, mix_g, out_g, poly_mix, po2):
         blob = np.ascontiguousarray(circuit_blob, np.uint32)
