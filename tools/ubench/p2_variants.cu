@@ -18,6 +18,33 @@ constexpr ShoupTables make_shoup() {
 }
 __constant__ ShoupTables c_shoup = make_shoup();
 
+// Montgomery product with the m*P step forced onto IMAD.WIDE (64-bit accumulate) instead of IMAD.HI: the low word of
+// t + m*P is zero by construction; adding it to the high word keeps it live so ptxas cannot narrow the op to IMAD.HI.
+__device__ __forceinline__ uint32_t mont_wide_lazy(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = (uint32_t)t * 0x77ffffffu;
+  uint64_t s;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(s) : "r"(m), "r"(P), "l"(t));
+  return (uint32_t)(s >> 32) + (uint32_t)s;
+}
+__device__ __forceinline__ uint32_t sbox7_wide(uint32_t x) {
+  uint32_t x2 = reduce_2p(mont_wide_lazy(x, x));
+  uint32_t x4 = mont_wide_lazy(x2, x2);
+  uint32_t x6 = mont_wide_lazy(x4, x2);
+  return reduce_2p(mont_wide_lazy(x6, x));
+}
+// subtractive form: r = hi(t) - hi(m' P) in (-P, P), one conditional +P; lazy variant keeps the signed value
+__device__ __forceinline__ uint32_t sbox7_sub(uint32_t x) {
+  auto mm = [](uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; uint32_t m = (uint32_t)t * 0x88000001u; uint32_t r = (uint32_t)(t >> 32) - __umulhi(m, P); return min(r, r + P); };
+  uint32_t x2 = mm(x, x), x3 = mm(x2, x), x4 = mm(x2, x2);
+  return mm(x3, x4);
+}
+// subtractive Montgomery with a PLAIN IMAD.HI (no 64-bit addend): canonical = 5 instr, lazy (0, 2P) = 4 instr (IADD3 hi - u + P)
+__device__ __forceinline__ uint32_t mm_c(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; uint32_t m = (uint32_t)t * 0x88000001u; uint32_t r = (uint32_t)(t >> 32) - __umulhi(m, P); return min(r, r + P); }
+__device__ __forceinline__ uint32_t mm_l(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; uint32_t m = (uint32_t)t * 0x88000001u; return (uint32_t)(t >> 32) - __umulhi(m, P) + P; }
+__device__ __forceinline__ uint32_t sbox7_sub_lazy(uint32_t x) { uint32_t x2 = mm_c(x, x), x4 = mm_l(x2, x2), x6 = mm_l(x4, x2); return mm_c(x6, x); }
+__device__ __forceinline__ uint32_t sbox7_sub_d3(uint32_t x) { uint32_t x2 = mm_c(x, x), x3 = mm_l(x2, x), x4 = mm_c(x2, x2); return mm_c(x3, x4); }
+template <int SB> __device__ __forceinline__ uint32_t sbox_sel(uint32_t x) { return SB == 1 ? sbox7_wide(x) : SB == 2 ? sbox7_sub(x) : SB == 3 ? sbox7_sub_lazy(x) : SB == 4 ? sbox7_sub_d3(x) : p2::sbox7(x); }
 template <int ALU> __device__ __forceinline__ uint32_t addm(uint32_t a, uint32_t b) {
   uint32_t s = ALU ? a + b + c_zero : a + b;
   return min(s, s - P);
@@ -94,6 +121,41 @@ template <int V> __device__ __forceinline__ void permute_v(uint32_t* s) {
   }
 }
 
+template <int SB> __device__ __forceinline__ void permute_sb(uint32_t* s) {
+  const auto& T = ZKB_P2_TABLES;
+  m_extv<0>(s);
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<0>(s[i], T.ext[r * 24 + i]));
+    m_extv<0>(s);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 21; ++r) {
+    s[0] = sbox_sel<SB>(addm<0>(reduce_2p(s[0]), T.in[r]));
+    uint64_t a0 = 0, a1 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { a0 += s[i]; a1 += s[12 + i]; }
+    uint32_t t0 = addm<0>(reduce_2p(reduce_2p((uint32_t)a0)), reduce_2p((uint32_t)(a0 >> 32) * R_MOD_P));
+    uint32_t t1 = addm<0>(reduce_2p(reduce_2p((uint32_t)a1)), reduce_2p((uint32_t)(a1 >> 32) * R_MOD_P));
+    uint32_t tot = addm<0>(t0, t1);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      uint32_t q = __umulhi(s[i], c_shoup.dq[i]);
+      uint32_t rr = s[i] * c_shoup.d[i] - q * P;
+      s[i] = tot + reduce_2p(rr);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
+#pragma unroll 1
+  for (int r = 4; r < 8; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<0>(s[i], T.ext[r * 24 + i]));
+    m_extv<0>(s);
+  }
+}
+
 constexpr int REPS = 14;
 #define DUAL_HERE
    // permutations per thread (a 224-column row)
@@ -106,7 +168,7 @@ template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32
   for (int rep = 0; rep < REPS; ++rep) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
-    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else permute_v<(V < 0 ? 0 : V)>(s);
+    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 100) permute_sb<(V >= 100 ? V - 100 : 0)>(s); else permute_v<(V < 0 || V >= 100 ? 0 : V)>(s);
   }
   uint4* o = reinterpret_cast<uint4*>(out + (size_t)gid * 8);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]); o[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -234,6 +296,14 @@ template <int A1, int A2, int BLOCK> void run_dual(const char* name) {
   cudaFree(out);
 }
 int main() {
+  run<-1, 128>("baseline (library permute)");
+  run<100, 128>("sb0: library sbox in local permute");
+  run<101, 128>("sb1: m*P via IMAD.WIDE (forced)");
+  run<102, 128>("sb2: subtractive form, x3*x4 chain");
+  run<103, 128>("sb3: subtractive, lazy x4/x6 (18 instr)");
+  run<104, 128>("sb4: subtractive, depth-3 chain (19 instr)");
+  run<103, 256>("sb3: subtractive, lazy x4/x6 (18 instr)");
+  return 0;
   run_dual<0, 0, 128>("dual, shoup+lazy");
   run_dual<0, 0, 64>("dual, shoup+lazy");
   run_dual<0, 0, 256>("dual, shoup+lazy");

@@ -24,17 +24,36 @@ constexpr uint32_t R_MOD_P = 0x0ffffffeu;    // Montgomery form of 1
 constexpr uint32_t R2_MOD_P = 1172168163u;   // 2^64 mod P
 constexpr uint32_t INVALID = 0xffffffffu;
 
-// Montgomery reduction of a 64-bit value t < P * 2^32: returns t / 2^32 mod P in [0, 2P).
+constexpr uint32_t P_INV = 0x88000001u;      // P^{-1} mod 2^32 (= 2^31 + 2^27 + 1)
+ZKB_HD uint32_t mul_hi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// Montgomery reduction of a 64-bit value t < P * 2^32, SUBTRACTIVE form: with m = lo(t) * P^{-1} the low words of t and
+// m * P agree, so t / 2^32 = hi(t) - hi(m * P) exactly, a value in (-P, P).  On sm_100a this is IMAD + a plain IMAD.HI + one
+// IADD3; the additive form (t + m' P) >> 32 compiles to an IMAD.HI with a 64-bit addend, which measures ~4 % slower over
+// a whole Poseidon2 permutation (profiles/r1_ubench_p2_variants.txt).
+//   mont_redc_lazy: hi - u + P, in (0, 2P)  (one 3-input add);   reduce_2p brings it to [0, P).
 ZKB_HD uint32_t mont_redc_lazy(uint64_t t) {
-  uint32_t m = (uint32_t)t * P_NEG_INV;
-  return (uint32_t)((t + (uint64_t)m * P) >> 32);
+  uint32_t m = (uint32_t)t * P_INV;
+  return (uint32_t)(t >> 32) - mul_hi32(m, P) + P;
 }
 ZKB_HD uint32_t reduce_2p(uint32_t x) {      // [0, 2P) -> [0, P)
   uint32_t y = x - P;
-  return y < x ? y : x;                        // unsigned min: IADD3 + IMNMX.U32
+  return y < x ? y : x;                        // unsigned min: VIADDMNMX.U32
 }
-ZKB_HD uint32_t mont_mul(uint32_t a, uint32_t b) { return reduce_2p(mont_redc_lazy((uint64_t)a * b)); }
-// product left in [0, 2P); valid when a * b < P * 2^32 (e.g. a < 2P, b < P)
+// canonical product; valid when a * b < P * 2^32 (e.g. a < 2P, b < P): r = hi - u in (-P, P), then one conditional + P
+ZKB_HD uint32_t mont_mul(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = (uint32_t)t * P_INV;
+  uint32_t r = (uint32_t)(t >> 32) - mul_hi32(m, P);
+  uint32_t y = r + P;
+  return y < r ? y : r;                        // r "negative" (wrapped)  <=>  r + P wraps back below r
+}
+// product left in (0, 2P); same precondition
 ZKB_HD uint32_t mont_mul_lazy(uint32_t a, uint32_t b) { return mont_redc_lazy((uint64_t)a * b); }
 ZKB_HD uint32_t add_mod(uint32_t a, uint32_t b) { return reduce_2p(a + b); }
 ZKB_HD uint32_t sub_mod(uint32_t a, uint32_t b) {

@@ -89,8 +89,8 @@ typedef unsigned int u32; typedef unsigned long long u64;
 #define P 2013265921u
 #define NB 1073741848u   /* Montgomery form of -11 (Fp4 = Fp[x]/(x^4+11)) */
 __device__ __forceinline__ u32 red(u32 x) { return min(x, x - P); }
-__device__ __forceinline__ u32 mull(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x77ffffffu; return (u32)((t + (u64)m * P) >> 32); }
-__device__ __forceinline__ u32 mul(u32 a, u32 b) { return red(mull(a, b)); }
+__device__ __forceinline__ u32 mull(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; return (u32)(t >> 32) - __umulhi(m, P) + P; }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; u32 r = (u32)(t >> 32) - __umulhi(m, P); return min(r, r + P); }
 __device__ __forceinline__ u32 add(u32 a, u32 b) { return red(a + b); }
 __device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return min(d, d + P); }
 struct F4 { u32 a, b, c, d; };
@@ -108,7 +108,7 @@ __device__ __forceinline__ F4 tof4(uint4 w) { F4 r; r.a = w.x; r.b = w.y; r.c = 
 // accumulator below P * 2^32 + 2 P^2 < 2^64; a single Montgomery reduction at the end of the chain gives the canonical
 // word.  An accumulator that continues from a canonical value m starts as m << 32 (= m * R).
 __device__ __forceinline__ u64 fixhi(u64 a) { u32 hi = (u32)(a >> 32); hi = min(hi, hi - P); return ((u64)hi << 32) | (u32)a; }
-__device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x77ffffffu; return red((u32)((a + (u64)m * P) >> 32)); }
+__device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x88000001u; u32 r = (u32)(a >> 32) - __umulhi(m, P); return min(r, r + P); }
 __device__ __forceinline__ F4 scale4(F4 x, u32 s) { F4 r; r.a = mul(x.a, s); r.b = mul(x.b, s); r.c = mul(x.c, s); r.d = mul(x.d, s); return r; }
 __device__ __forceinline__ F4 add4(F4 x, F4 y) { F4 r; r.a = add(x.a, y.a); r.b = add(x.b, y.b); r.c = add(x.c, y.c); r.d = add(x.d, y.d); return r; }
 )";
