@@ -134,6 +134,8 @@ struct EvalJitCache {
 };
 
 static int min_blocks();
+static uint32_t ec_batch() { const char* e = getenv("ZKB_EC_BATCH"); int v = e ? atoi(e) : 4; return (uint32_t)(v < 1 ? 1 : v > 4096 ? 4096 : v); }
+static uint32_t ec_prefetch() { const char* e = getenv("ZKB_EC_PREFETCH"); int v = e ? atoi(e) : 1; return (uint32_t)(v < 0 ? 0 : v > 8 ? 8 : v); }
 // Per-proof kernel data: [powers of poly_mix, 4 words each][mix globals][out globals].  It lives in the module's
 // __constant__ bank when it fits (operands then come straight from the constant cache), else behind a pointer.
 constexpr size_t CONST_WORDS_MAX = 15 * 1024;
@@ -194,12 +196,47 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
     o << "  F4 m" << id << "; m" << id << ".a = fin(A" << a << "_0); m" << id << ".b = fin(A" << a << "_1); m" << id << ".c = fin(A" << a << "_2); m" << id << ".d = fin(A" << a << "_3);\n";
     state[id] = ST_CANON;
   };
+  // Load scheduling.  The kernel is bound by global-load latency (ncu: 87 % long-scoreboard stalls when every tap is loaded
+  // right before its use), so the tap loads of the next `batch` constraints are hoisted in front of the arithmetic of the
+  // current ones (software pipelining, distance `prefetch` batches); a tap needed twice within the hoisted group is loaded once.
+  const uint32_t batch = ec_batch(), prefetch = ec_prefetch();
+  std::vector<uint32_t> get_batch(n, 0);
+  uint32_t n_batches = 1;
+  {
+    uint32_t live_mix = 0, mj = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const StepDef& s = c.steps[i];
+      if (s.op <= PX_MUL) { get_batch[i] = live_mix / batch; continue; }
+      uint32_t id = mj++;
+      if (s.op != PX_TRUE && mx_used[id]) ++live_mix;
+    }
+    n_batches = live_mix / batch + 1;
+  }
+  std::vector<std::vector<size_t>> gets_of(n_batches + 1);
+  for (size_t i = 0; i < n; ++i) if (c.steps[i].op == PX_GET && fp_used[fp_of[i]]) gets_of[std::min<uint32_t>(get_batch[i], n_batches)].push_back(i);
+  std::vector<char> get_done(n, 0);
+  auto hoist = [&](uint32_t b) {
+    if (b >= gets_of.size()) return;
+    std::map<uint32_t, uint32_t> seen;       // tap -> fp id, within this group
+    for (size_t i : gets_of[b]) {
+      const StepDef& s = c.steps[i];
+      auto it = seen.find(s.a);
+      if (it != seen.end()) { o << "  const u32 f" << fp_of[i] << " = f" << it->second << ";\n"; }
+      else { const TapDef& t = c.taps[s.a]; o << "  const u32 f" << fp_of[i] << " = TAP(g" << t.group << ", " << t.column << ", " << t.back << ");\n"; seen[s.a] = fp_of[i]; }
+      get_done[i] = 1;
+    }
+  };
+  uint32_t hoisted_upto = 0;                  // batches [0, hoisted_upto) have had their loads emitted
+  auto hoist_until = [&](uint32_t b_end) { while (hoisted_upto < b_end && hoisted_upto < gets_of.size()) hoist(hoisted_upto++); };
+  hoist_until(1 + prefetch);
+  uint32_t live_seen = 0;
   uint32_t fi = 0, mi = 0;
   for (size_t i = 0; i < n; ++i) {
     const StepDef& s = c.steps[i];
     if (s.op <= PX_MUL) {
       uint32_t id = fi++;
       if (!fp_used[id]) continue;
+      if (s.op == PX_GET && get_done[i]) continue;
       o << "  const u32 f" << id << " = ";
       switch (s.op) {
         case PX_CONST: o << Fp::from(s.a).v << "u"; break;
@@ -215,6 +252,8 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
     uint32_t id = mi++;
     if (s.op == PX_TRUE) { state[id] = ST_ZERO; continue; }
     if (!mx_used[id]) continue;
+    ++live_seen;
+    if (live_seen % batch == 0) hoist_until(live_seen / batch + 1 + prefetch);      // entering the next batch: start the loads `prefetch` batches ahead
     if (s.op == PX_AND_EQZ) {
       const uint32_t base = s.a, k = mx_pow[base];
       uint32_t set, terms;
