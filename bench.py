@@ -301,15 +301,22 @@ def main():
         alg_bytes = 4 * rows * cols + 32 * rows
         achieved = alg_bytes / (ms * 1e-3) / 1e9
         perms = rows * ((cols + 15) // 16)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_h_hash_rows_traffic.json")     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+        if po2 == PO2 and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
         roof = {"bound": "hbm", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind, "ms_per_launch": ms,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
+                "peak_source": peak_kind, "ms_per_launch": ms,
                 "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation; peak = measured "
                                   "pure Montgomery-modmul stream on B200 (profiles/r1_ubench_fp64_mix.txt)",
                           "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3), "peak_modmul_per_s": INT32_MODMUL_PEAK,
                           "frac": 1356 * perms / (ms * 1e-3) / INT32_MODMUL_PEAK}}
         del mat, dig
         # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT and x4 LDE over 64 columns of 2^20
-        ntt_cols = 64
+        ntt_cols = 224
         buf = hal.alloc_elem(ntt_cols * n); big = hal.alloc_elem(ntt_cols * 4 * n)
         for _ in range(2):
             hal.batch_interpolate_ntt_zk_shift(buf, ntt_cols); hal.batch_expand_into_evaluate_ntt(big, buf, ntt_cols, 2)
@@ -321,8 +328,13 @@ def main():
         for _ in range(reps):
             hal.batch_expand_into_evaluate_ntt(big, buf, ntt_cols, 2)
         ms_l = hal.timer_stop() / reps
-        roof["ntt"] = {"intt_zk_shift": {"cols": ntt_cols, "po2": po2, "ms": ms_i, "GBps": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9, "frac": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                       "lde_x4": {"cols": ntt_cols, "po2": po2, "ms": ms_l, "GBps": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9, "frac": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+        mm_i = ntt_cols * (n // 2) * po2 + ntt_cols * n            # butterflies + inter-pass twiddle / scale multiplications
+        mm_l = ntt_cols * 2 * n * po2 + ntt_cols * 4 * n
+        roof["ntt"] = {"intt_zk_shift": {"cols": ntt_cols, "po2": po2, "ms": ms_i, "GBps": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9, "frac": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                         "int32_frac": mm_i / (ms_i * 1e-3) / INT32_MODMUL_PEAK},
+                       "lde_x4": {"cols": ntt_cols, "po2": po2, "ms": ms_l, "GBps": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9, "frac": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                  "int32_frac": mm_l / (ms_l * 1e-3) / INT32_MODMUL_PEAK},
+                       "note": "NTT GB/s on algorithmic bytes (8 n c / 20 n c); above n ~ 2^12 the butterflies are INT32-pipe bound, hence int32_frac"}
         del buf, big
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------------------

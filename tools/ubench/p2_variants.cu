@@ -121,18 +121,18 @@ template <int V> __device__ __forceinline__ void permute_v(uint32_t* s) {
   }
 }
 
-template <int SB> __device__ __forceinline__ void permute_sb(uint32_t* s) {
+template <int SB, int AL = 0> __device__ __forceinline__ void permute_sb(uint32_t* s) {
   const auto& T = ZKB_P2_TABLES;
-  m_extv<0>(s);
+  m_extv<AL>(s);
 #pragma unroll 1
   for (int r = 0; r < 4; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<0>(s[i], T.ext[r * 24 + i]));
-    m_extv<0>(s);
+    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<AL>(s[i], T.ext[r * 24 + i]));
+    m_extv<AL>(s);
   }
 #pragma unroll 1
   for (int r = 0; r < 21; ++r) {
-    s[0] = sbox_sel<SB>(addm<0>(reduce_2p(s[0]), T.in[r]));
+    s[0] = sbox_sel<SB>(addm<AL>(reduce_2p(s[0]), T.in[r]));
     uint64_t a0 = 0, a1 = 0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) { a0 += s[i]; a1 += s[12 + i]; }
@@ -143,7 +143,7 @@ template <int SB> __device__ __forceinline__ void permute_sb(uint32_t* s) {
     for (int i = 0; i < 24; ++i) {
       uint32_t q = __umulhi(s[i], c_shoup.dq[i]);
       uint32_t rr = s[i] * c_shoup.d[i] - q * P;
-      s[i] = tot + reduce_2p(rr);
+      s[i] = add_lazy<AL>(tot, reduce_2p(rr));
     }
   }
 #pragma unroll
@@ -151,8 +151,8 @@ template <int SB> __device__ __forceinline__ void permute_sb(uint32_t* s) {
 #pragma unroll 1
   for (int r = 4; r < 8; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<0>(s[i], T.ext[r * 24 + i]));
-    m_extv<0>(s);
+    for (int i = 0; i < 24; ++i) s[i] = sbox_sel<SB>(addm<AL>(s[i], T.ext[r * 24 + i]));
+    m_extv<AL>(s);
   }
 }
 
@@ -168,7 +168,7 @@ template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32
   for (int rep = 0; rep < REPS; ++rep) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
-    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 100) permute_sb<(V >= 100 ? V - 100 : 0)>(s); else permute_v<(V < 0 || V >= 100 ? 0 : V)>(s);
+    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 200) permute_sb<(V >= 200 ? V - 200 : 0), 1>(s); else if (V >= 100) permute_sb<(V >= 100 && V < 200 ? V - 100 : 0)>(s); else permute_v<(V < 0 || V >= 100 ? 0 : V)>(s);
   }
   uint4* o = reinterpret_cast<uint4*>(out + (size_t)gid * 8);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]); o[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -303,6 +303,8 @@ int main() {
   run<103, 128>("sb3: subtractive, lazy x4/x6 (18 instr)");
   run<104, 128>("sb4: subtractive, depth-3 chain (19 instr)");
   run<103, 256>("sb3: subtractive, lazy x4/x6 (18 instr)");
+  run<203, 128>("sb3 + all adds forced to IADD3 (ALU)");
+  run<203, 256>("sb3 + all adds forced to IADD3 (ALU)");
   return 0;
   run_dual<0, 0, 128>("dual, shoup+lazy");
   run_dual<0, 0, 64>("dual, shoup+lazy");
