@@ -40,6 +40,7 @@ void ntt_tables_free(zkb_ctx* ctx) {
   cudaFree(ctx->ntt->d_lo);
   for (auto& kv : ctx->ntt->level_tables) cudaFree(kv.second);
   for (auto& kv : ctx->ntt->shift_tables) cudaFree(kv.second);
+  for (auto& kv : ctx->ntt->s_tables) cudaFree(kv.second);
   delete ctx->ntt;
   ctx->ntt = nullptr;
 }

@@ -13,6 +13,7 @@ struct NttTables {
   Fp rou_fwd[MAX_ROU_PO2 + 1], rou_rev[MAX_ROU_PO2 + 1];
   std::map<int, uint32_t*> level_tables;   // keyed by (log2 size << 1 | inverse): per-level twiddles for tiled kernels
   std::map<uint64_t, uint32_t*> shift_tables;
+  std::map<uint64_t, uint32_t*> s_tables;      // strided-pass inter-pass factor tables (Shoup pairs), see k_ntt_s TAB
 };
 NttTables* ntt_tables(zkb_ctx* ctx);
 
