@@ -83,6 +83,11 @@ template <int N> __device__ __forceinline__ void canonicalize(uint32_t (&v)[N]) 
   for (int r = 0; r < N; ++r) v[r] = reduce_2p(v[r]);
 }
 
+// Shared-memory slot of register r in a round whose register field starts at bit SH of the (unpadded) tile index, given
+// pb = phys(x0) for the index x0 with r = 0: phys(x0 + (r << SH)) = pb + K + (K >> 4), K = r << SH, because the r-field of x0
+// is empty (no carry into or out of it).  K is a compile-time constant after unrolling, so every access is one LDS / STS with
+// an immediate offset instead of ~4 index instructions.
+__device__ __forceinline__ uint32_t phys_r(uint32_t pb, int r, int sh) { const uint32_t K = (uint32_t)r << sh; return pb + K + (K >> 4); }
 // local index of register r for thread t in a round whose register field starts at bit p
 __device__ __forceinline__ uint32_t local_index(uint32_t t, int p, int r) {
   uint32_t lo = t & ((1u << p) - 1u), hi = t >> p;
@@ -112,11 +117,12 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 #pragma unroll
   for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
     const int pc = p < 0 ? 0 : p;
+    const uint32_t pb_w = phys(soff + local_index(t, p_prev, 0)), pb_r = phys(soff + local_index(t, pc, 0));
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[phys(soff + local_index(t, p_prev, r))] = v[r];
+    for (int r = 0; r < 16; ++r) s[phys_r(pb_w, r, p_prev)] = v[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = s[phys(soff + local_index(t, pc, r))];
+    for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
     __syncthreads();
     if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
     else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
@@ -169,11 +175,12 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ 
 #pragma unroll
   for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
     const int pc = p > PLAST ? PLAST : p;
+    const uint32_t pb_w = phys(soff + local_index(t, p_prev, 0)), pb_r = phys(soff + local_index(t, pc, 0));
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[phys(soff + local_index(t, p_prev, r))] = v[r];
+    for (int r = 0; r < 16; ++r) s[phys_r(pb_w, r, p_prev)] = v[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = s[phys(soff + local_index(t, pc, r))];
+    for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
     __syncthreads();
     if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
     else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
@@ -216,8 +223,11 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   const size_t block = blockIdx.x >> args.tiles_per_block_log;
   const uint32_t p2 = (tile << T_LOG) + c2;                                 // position inside the row of S
   const int m_log = A + (int)args.s_log;
-  uint32_t* base = io + (block << m_log) + p2;
-  const size_t S = (size_t)1 << args.s_log;
+  uint32_t* const cb = io + (block << m_log);            // CTA-uniform; everything below is a 32-bit offset (< 2^26 elements)
+  const uint32_t s_log = args.s_log;
+  const uint32_t off_r = (t << s_log) + p2;                // element (r * TPB + t, p2): off_r + r * (TPB << s_log)
+  const uint32_t off_c = ((16u * t) << s_log) + p2;        // element (16 t + r, p2):   off_c + (r << s_log)
+  const uint32_t S = 1u << s_log;
   uint32_t v[16];
   constexpr int REM = A % 4;
 
@@ -225,10 +235,9 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   // G = w_M^(+-p2) [* shift base], V = G^(rev_{A-4}(t)), g = G^(2^(A-4)).
   auto twiddle_all = [&](bool inverse) {
     if (TAB) {
-      const uint2* trow = ttab + ((size_t)16 * t) * S + p2;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        uint32_t x = shoup_lazy(v[r], __ldg(trow + (size_t)r * S));
+        uint32_t x = shoup_lazy(v[r], __ldg(ttab + (off_c + ((uint32_t)r << s_log))));
         v[r] = inverse ? reduce_2p(x) : x;          // forward: the butterflies take lazy values; inverse: stored next
       }
       return;
@@ -252,17 +261,18 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   if (INV) {
     constexpr int P0 = A - 4;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = base[((size_t)r * TPB + t) * S];
+    for (int r = 0; r < 16; ++r) v[r] = cb[off_r + (((uint32_t)r * TPB) << s_log)];
     radix_round<true, 0, 4>(v, P0, t, twl);
     int p_prev = P0;
 #pragma unroll
     for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
       const int pc = p < 0 ? 0 : p;
+      const uint32_t pb_w = phys((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys((local_index(t, pc, 0) << T_LOG) + c2);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) sm[phys((local_index(t, p_prev, r) << T_LOG) + c2)] = v[r];
+      for (int r = 0; r < 16; ++r) sm[phys_r(pb_w, r, p_prev + T_LOG)] = v[r];
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = sm[phys((local_index(t, pc, r) << T_LOG) + c2)];
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys_r(pb_r, r, pc + T_LOG)];
       __syncthreads();
       if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
       else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
@@ -270,22 +280,23 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
     }
     twiddle_all(true);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) base[((size_t)16 * t + r) * S] = v[r];
+    for (int r = 0; r < 16; ++r) cb[off_c + ((uint32_t)r << s_log)] = v[r];
   } else {
     constexpr int PLAST = A - 4;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = base[((size_t)16 * t + r) * S];
+    for (int r = 0; r < 16; ++r) v[r] = cb[off_c + ((uint32_t)r << s_log)];
     twiddle_all(false);
     radix_round<false, 0, 4>(v, 0, 0u, twl);
     int p_prev = 0;
 #pragma unroll
     for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
       const int pc = p > PLAST ? PLAST : p;
+      const uint32_t pb_w = phys((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys((local_index(t, pc, 0) << T_LOG) + c2);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) sm[phys((local_index(t, p_prev, r) << T_LOG) + c2)] = v[r];
+      for (int r = 0; r < 16; ++r) sm[phys_r(pb_w, r, p_prev + T_LOG)] = v[r];
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = sm[phys((local_index(t, pc, r) << T_LOG) + c2)];
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys_r(pb_r, r, pc + T_LOG)];
       __syncthreads();
       if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
       else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
     }
     canonicalize(v);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) base[((size_t)r * TPB + t) * S] = v[r];
+    for (int r = 0; r < 16; ++r) cb[off_r + (((uint32_t)r * TPB) << s_log)] = v[r];
   }
 }
 
