@@ -16,6 +16,17 @@ inline Fp4Arg to_arg(const uint32_t* w) { Fp4Arg a; memcpy(a.w, w, 16); return a
 
 constexpr int EW_BLOCK = 256;
 
+// Lazy sums of products: a 64-bit accumulator takes unreduced 32 x 32-bit products (one IMAD.WIDE each); after every second
+// product its high word is brought back below P, which keeps it below P * 2^32 + 2 P^2 < 2^64; fin_acc does the one
+// Montgomery reduction at the end.
+__device__ __forceinline__ uint64_t fixhi(uint64_t a) {       // high word < 2P  ->  high word < P (value mod P unchanged)
+  uint32_t hi = (uint32_t)(a >> 32);
+  uint32_t y = hi - P;
+  hi = y < hi ? y : hi;
+  return ((uint64_t)hi << 32) | (uint32_t)a;
+}
+__device__ __forceinline__ uint32_t fin_acc(uint64_t a) { return reduce_2p(mont_redc_lazy(fixhi(a))); }
+
 // ---- trivial element-wise ----------------------------------------------------------------------------
 __global__ void k_add(uint32_t* __restrict__ o, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,7 +147,9 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict_
   const uint32_t combo = blockIdx.y;
   size_t idx = (size_t)blockIdx.x * EW_BLOCK + threadIdx.x;
   bool live = idx < count;
-  Fp4 acc;
+  // lazy 64-bit accumulation (see fixhi): one IMAD.WIDE per column and Fp4 component, one high-word fix per two columns
+  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  uint32_t terms = 0;
   bool any = false;
   for (uint32_t base = 0; base < input_size; base += MIX_CHUNK) {
     uint32_t chunk = min((uint32_t)MIX_CHUNK, input_size - base);
@@ -147,15 +160,16 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict_
     for (uint32_t t = 0; t < chunk; ++t) {
       if (s_combo[t] != combo) continue;      // uniform across the block
       uint4 p = s_pw[t];
-      Fp v = Fp::raw(__ldg(in + (size_t)(base + t) * count + idx));
-      acc += ld4(p) * v;
+      uint32_t v = __ldg(in + (size_t)(base + t) * count + idx);
+      a0 += (uint64_t)v * p.x; a1 += (uint64_t)v * p.y; a2 += (uint64_t)v * p.z; a3 += (uint64_t)v * p.w;
       any = true;
+      if (++terms == 2) { a0 = fixhi(a0); a1 = fixhi(a1); a2 = fixhi(a2); a3 = fixhi(a3); terms = 0; }
     }
   }
   if (live && any) {
     uint4* o = out + (size_t)combo * count + idx;
     uint4 cur = *o;
-    Fp4 r = ld4(cur) + acc;
+    Fp4 r = ld4(cur) + Fp4::raw(fin_acc(a0), fin_acc(a1), fin_acc(a2), fin_acc(a3));
     *o = st4(r);
   }
 }
@@ -181,13 +195,6 @@ __global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restric
   Fp4 r = pow(ld4(xv), exp);
   tables[g] = st4(r);
 }
-__device__ __forceinline__ uint64_t fixhi(uint64_t a) {       // high word < 2P  ->  high word < P (value mod P unchanged)
-  uint32_t hi = (uint32_t)(a >> 32);
-  uint32_t y = hi - P;
-  hi = y < hi ? y : hi;
-  return ((uint64_t)hi << 32) | (uint32_t)a;
-}
-__device__ __forceinline__ uint32_t fin_acc(uint64_t a) { return reduce_2p(mont_redc_lazy(fixhi(a))); }
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__ partial, const uint32_t* __restrict__ coeffs, size_t n,
                                                               const uint32_t* __restrict__ which, const uint4* __restrict__ tables, uint32_t n_slabs) {
   __shared__ uint4 s_pw[EVAL_STEPS];

@@ -12,8 +12,9 @@ namespace zkb {
 constexpr int HASH_BLOCK = 128;
 
 // out[r] = unpadded_hash(matrix[0*rows + r], matrix[1*rows + r], ...)   (rate 16, overwrite mode, zero pad)
-__global__ void __launch_bounds__(HASH_BLOCK) k_hash_rows(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, uint32_t cols) {
-  size_t r = (size_t)blockIdx.x * HASH_BLOCK + threadIdx.x;
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_hash_rows(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, uint32_t cols) {
+  size_t r = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (r >= rows) return;
   uint32_t s[24];
 #pragma unroll
@@ -67,7 +68,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_merkle_tail(uint32_t* __restri
 
 void hash_rows(zkb_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return;
-  k_hash_rows<<<grid_for(rows, HASH_BLOCK), HASH_BLOCK, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols);
+  static int block = [] { const char* e = getenv("ZKB_HASH_BLOCK"); return e ? atoi(e) : 256; }();
+  if (block == 256) k_hash_rows<256><<<grid_for(rows, 256), 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols);
+  else if (block == 64) k_hash_rows<64><<<grid_for(rows, 64), 64, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols);
+  else if (block == 128) k_hash_rows<128><<<grid_for(rows, 128), 128, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols);
+  else k_hash_rows<256><<<grid_for(rows, 256), 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols);
   launched(ctx);
 }
 void hash_fold(zkb_ctx* ctx, uint32_t* nodes, size_t input_size, size_t output_size) {
