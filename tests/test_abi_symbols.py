@@ -46,3 +46,13 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "#include \"../../oracle" not in src, f
+
+
+def test_generated_rust_bindings_are_current():
+    """integration/rust/zkb200-sys/src/lib.rs is generated from the header (tools/gen_rust_ffi.py) and must not drift."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    src, names = mod.generate()
+    assert sorted(names) == header_symbols()
+    assert open(os.path.join(ROOT, "integration", "rust", "zkb200-sys", "src", "lib.rs")).read() == src, "run python tools/gen_rust_ffi.py"
