@@ -30,6 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ORIG_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
 METRIC = "segments proven/sec (2^20 cycles)"
 UNIT = "segments/s"
 PO2 = 20
@@ -98,7 +99,10 @@ def cpu_baseline(sample_po2, threads=None):
     """The oracle prover (restated CpuHal) on a SYN-280 segment of 2^sample_po2 cycles, all host threads."""
     from zktls_b200 import circuit, synth
     from oracle import oracle as O
-    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers) and wherever the GPU arm
+    # pinned this process
+    if ORIG_AFFINITY:
+        os.sched_setaffinity(0, ORIG_AFFINITY)
     O.lib().orc_set_num_threads(int(threads) if threads else (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()))
     cores = O.lib().orc_num_threads()
     blob = circuit.syn_circuit(**circuit.SYN280).blob()
@@ -137,6 +141,23 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_rank_to_gpu_numa_node(index):
+    """Best effort: run this rank's host threads (and so first-touch its pinned trace buffers) on the CPUs NVML reports as
+    local to its GPU, so that with 8 ranks the 8 x 1.17 GB uploads per step do not all cross one socket's memory controller."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:       # noqa: BLE001
+        pass
+
+
 def workload_config():
     return {"workload": "syn280-segment-po2-20: one synthetic 2^20-cycle rv32im-shaped segment (BASELINE.json configs[1]): iNTT+zk-shift, x4 LDE, "
                         "Poseidon2 Merkle commit of code/data/accum/check, eval_check, DEEP + mix + divide, 3 FRI rounds, 50 queries; seal on host",
@@ -172,6 +193,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    pin_rank_to_gpu_numa_node(local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout; stdout carries exactly one JSON line
