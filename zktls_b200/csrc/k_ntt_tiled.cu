@@ -88,6 +88,12 @@ template <int N> __device__ __forceinline__ void canonicalize(uint32_t (&v)[N]) 
 // is empty (no carry into or out of it).  K is a compile-time constant after unrolling, so every access is one LDS / STS with
 // an immediate offset instead of ~4 index instructions.
 __device__ __forceinline__ uint32_t phys_r(uint32_t pb, int r, int sh) { const uint32_t K = (uint32_t)r << sh; return pb + K + (K >> 4); }
+// Strided pass: the tile is (rows x 2^TL); padding adds 2^TL words per 16 rows (same footprint as phys).  A warp holds
+// 2^(5-TL) consecutive threads-in-column x 2^TL columns: when their rows are 16 apart (round p = 0) the pad moves each onto its
+// own group of banks, and when they are consecutive rows the pad is constant across the warp, so every round is conflict-free
+// (phys(), whose pad changes every 16 WORDS, made neighbouring rows collide once the tile became 8 wide: 88 M conflict cycles).
+template <int TL> __device__ __forceinline__ uint32_t phys_t(uint32_t x) { return x + ((x >> (4 + TL)) << TL); }
+template <int TL> __device__ __forceinline__ uint32_t phys_tr(uint32_t pb, int r, int sh) { const uint32_t K = (uint32_t)r << sh; return pb + K + ((K >> (4 + TL)) << TL); }
 // local index of register r for thread t in a round whose register field starts at bit p
 __device__ __forceinline__ uint32_t local_index(uint32_t t, int p, int r) {
   uint32_t lo = t & ((1u << p) - 1u), hi = t >> p;
@@ -267,12 +273,12 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
 #pragma unroll
     for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
       const int pc = p < 0 ? 0 : p;
-      const uint32_t pb_w = phys((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys((local_index(t, pc, 0) << T_LOG) + c2);
+      const uint32_t pb_w = phys_t<T_LOG>((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys_t<T_LOG>((local_index(t, pc, 0) << T_LOG) + c2);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) sm[phys_r(pb_w, r, p_prev + T_LOG)] = v[r];
+      for (int r = 0; r < 16; ++r) sm[phys_tr<T_LOG>(pb_w, r, p_prev + T_LOG)] = v[r];
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = sm[phys_r(pb_r, r, pc + T_LOG)];
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys_tr<T_LOG>(pb_r, r, pc + T_LOG)];
       __syncthreads();
       if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
       else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
@@ -291,12 +297,12 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
 #pragma unroll
     for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
       const int pc = p > PLAST ? PLAST : p;
-      const uint32_t pb_w = phys((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys((local_index(t, pc, 0) << T_LOG) + c2);
+      const uint32_t pb_w = phys_t<T_LOG>((local_index(t, p_prev, 0) << T_LOG) + c2), pb_r = phys_t<T_LOG>((local_index(t, pc, 0) << T_LOG) + c2);
 #pragma unroll
-      for (int r = 0; r < 16; ++r) sm[phys_r(pb_w, r, p_prev + T_LOG)] = v[r];
+      for (int r = 0; r < 16; ++r) sm[phys_tr<T_LOG>(pb_w, r, p_prev + T_LOG)] = v[r];
       __syncthreads();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = sm[phys_r(pb_r, r, pc + T_LOG)];
+      for (int r = 0; r < 16; ++r) v[r] = sm[phys_tr<T_LOG>(pb_r, r, pc + T_LOG)];
       __syncthreads();
       if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
       else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
