@@ -1,0 +1,128 @@
+// Poseidon2 pipe-assignment experiment (sm_100a): ptxas turns ~13 % of the permutation's additions into IMAD.IADD, which
+// issue on the multiplier pipe the s-boxes already saturate.  These variants keep every addition on the ALU pipe by
+// making it a genuine 3-input IADD3: either `hi - u + P` (canonical product = reduce_2p of the lazy form) or `a + b + z`
+// with z an opaque zero held in a REGISTER (kernel argument), not a constant-bank operand.
+//   bit0: canonical Montgomery product as reduce_2p(lazy)         bit1: a + b + z in add_mod around the s-boxes
+//   bit2: a + b + z inside the external linear layer              bit3: a + b + z in the internal rounds
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "../../zktls_b200/csrc/poseidon2.cuh"
+using namespace zkb;
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+template <int Z> __device__ __forceinline__ uint32_t addz(uint32_t a, uint32_t b, uint32_t z) { return Z ? a + b + z : a + b; }
+template <int Z> __device__ __forceinline__ uint32_t addm(uint32_t a, uint32_t b, uint32_t z) { return reduce_2p(addz<Z>(a, b, z)); }
+template <int C> __device__ __forceinline__ uint32_t mmc(uint32_t a, uint32_t b) { return C ? reduce_2p(mont_mul_lazy(a, b)) : mont_mul(a, b); }
+template <int C> __device__ __forceinline__ uint32_t sbox(uint32_t x) {
+  uint32_t x2 = mmc<C>(x, x), x4 = mont_mul_lazy(x2, x2), x6 = mont_mul_lazy(x4, x2);
+  return mmc<C>(x6, x);
+}
+template <int Z> __device__ __forceinline__ void m4z(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t z) {
+  uint32_t t0 = addm<Z>(x0, x1, z), t1 = addm<Z>(x2, x3, z);
+  uint32_t t2 = addm<Z>(addm<Z>(x1, x1, z), t1, z), t3 = addm<Z>(addm<Z>(x3, x3, z), t0, z);
+  uint32_t t1_2 = addm<Z>(t1, t1, z), t0_2 = addm<Z>(t0, t0, z);
+  uint32_t t4 = addm<Z>(addm<Z>(t1_2, t1_2, z), t3, z), t5 = addm<Z>(addm<Z>(t0_2, t0_2, z), t2, z);
+  x0 = addm<Z>(t3, t5, z); x1 = t5; x2 = addm<Z>(t2, t4, z); x3 = t4;
+}
+template <int Z> __device__ __forceinline__ void mext(uint32_t* s, uint32_t z) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c) m4z<Z>(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3], z);
+  uint32_t sums[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t a = addm<Z>(s[k], s[4 + k], z), b = addm<Z>(s[8 + k], s[12 + k], z), c = addm<Z>(s[16 + k], s[20 + k], z);
+    sums[k] = addm<Z>(addm<Z>(a, b, z), c, z);
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = addm<Z>(s[i], sums[i & 3], z);
+}
+template <int V> __device__ __forceinline__ void permute_v(uint32_t* s, uint32_t z) {
+  constexpr int C = V & 1, Z1 = (V >> 1) & 1, Z2 = (V >> 2) & 1, Z3 = (V >> 3) & 1;
+  const auto& T = ZKB_P2_TABLES;
+  mext<Z2>(s, z);
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sbox<C>(addm<Z1>(s[i], T.ext[r * 24 + i], z));
+    mext<Z2>(s, z);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 21; ++r) {
+    s[0] = sbox<C>(addm<Z1>(reduce_2p(s[0]), T.in[r], z));
+    uint32_t tot = addm<Z3>(p2::sum12(s), p2::sum12(s + 12), z);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = addz<Z3>(tot, reduce_2p(p2::shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])), z);
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
+#pragma unroll 1
+  for (int r = 4; r < 8; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sbox<C>(addm<Z1>(s[i], T.ext[r * 24 + i], z));
+    mext<Z2>(s, z);
+  }
+}
+
+constexpr int REPS = 14;       // permutations per thread (a 224-column row)
+template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32_t* out, uint32_t seed, uint32_t z) {
+  uint32_t s[24];
+  uint32_t gid = blockIdx.x * BLOCK + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = 0;
+#pragma unroll 1
+  for (int rep = 0; rep < REPS; ++rep) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
+    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else permute_v<(V < 0 ? 0 : V)>(s, z);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)gid * 8);
+  o[0] = make_uint4(s[0], s[1], s[2], s[3]); o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+}
+static void host_ref(uint32_t gid, uint32_t seed, uint32_t* out8) {
+  uint32_t s[24] = {0};
+  for (int rep = 0; rep < REPS; ++rep) {
+    for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
+    p2::permute_host(s);
+  }
+  for (int i = 0; i < 8; ++i) out8[i] = s[i];
+}
+template <int V, int BLOCK> void run(const char* name) {
+  const size_t threads = (size_t)1 << 22;
+  uint32_t* out; CHECK(cudaMalloc(&out, threads * 32));
+  int occ = 0; CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern<V, BLOCK>, BLOCK, 0));
+  cudaFuncAttributes fa; CHECK(cudaFuncGetAttributes(&fa, kern<V, BLOCK>));
+  kern<V, BLOCK><<<threads / BLOCK, BLOCK>>>(out, 7, 0); CHECK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < 3; ++i) kern<V, BLOCK><<<threads / BLOCK, BLOCK>>>(out, 7, 0);
+  cudaEventRecord(e1); CHECK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+  uint32_t h[8], ref[8]; bool ok = true;
+  size_t probes[4] = {0, 12345, threads / 2 + 17, threads - 1};
+  for (int p = 0; p < 4; ++p) {
+    CHECK(cudaMemcpy(h, out + probes[p] * 8, 32, cudaMemcpyDeviceToHost));
+    host_ref((uint32_t)probes[p], 7, ref);
+    for (int i = 0; i < 8; ++i) ok = ok && (h[i] == ref[i]);
+  }
+  double perms = (double)threads * REPS;
+  printf("%-52s block %4d regs %3d occ %2d  %8.3f ms  %7.3f Gperm/s  %6.3f T modmul/s  %s\n", name, BLOCK, fa.numRegs, occ, ms, perms / ms / 1e6, perms * 1356 / ms / 1e9, ok ? "OK" : "MISMATCH");
+  cudaFree(out);
+}
+int main() {
+  run<-1, 128>("baseline (library permute)");
+  run<0, 128>("v0 same formulation, local code");
+  run<1, 128>("v1 canonical product = reduce_2p(lazy)");
+  run<2, 128>("v2 a+b+z around s-boxes");
+  run<3, 128>("v3 = v1 + v2");
+  run<4, 128>("v4 a+b+z in external linear layer");
+  run<7, 128>("v7 = v1 + v2 + v4");
+  run<8, 128>("v8 a+b+z in internal rounds");
+  run<15, 128>("v15 all");
+  run<9, 128>("v9 = v1 + v8");
+  run<11, 128>("v11 = v1 + v2 + v8");
+  run<15, 256>("v15 all");
+  run<7, 256>("v7");
+  return 0;
+}

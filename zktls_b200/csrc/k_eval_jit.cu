@@ -24,6 +24,7 @@
 #include <fstream>
 #include <sstream>
 #include <mutex>
+#include <set>
 
 namespace zkb {
 
@@ -89,29 +90,76 @@ typedef unsigned int u32; typedef unsigned long long u64;
 #define P 2013265921u
 #define NB 1073741848u   /* Montgomery form of -11 (Fp4 = Fp[x]/(x^4+11)) */
 __device__ __forceinline__ u32 red(u32 x) { return min(x, x - P); }
-__device__ __forceinline__ u32 mull(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; return (u32)(t >> 32) - __umulhi(m, P) + P; }
 __device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; u32 r = (u32)(t >> 32) - __umulhi(m, P); return min(r, r + P); }
 __device__ __forceinline__ u32 add(u32 a, u32 b) { return red(a + b); }
 __device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return min(d, d + P); }
-struct F4 { u32 a, b, c, d; };
-__device__ __forceinline__ F4 mul4(F4 x, F4 y) {
-  F4 r;
-  r.a = add(mul(x.a, y.a), mul(NB, add(add(mul(x.b, y.d), mul(x.c, y.c)), mul(x.d, y.b))));
-  r.b = add(add(mul(x.a, y.b), mul(x.b, y.a)), mul(NB, add(mul(x.c, y.d), mul(x.d, y.c))));
-  r.c = add(add(add(mul(x.a, y.c), mul(x.b, y.b)), mul(x.c, y.a)), mul(NB, mul(x.d, y.d)));
-  r.d = add(add(add(mul(x.a, y.d), mul(x.b, y.c)), mul(x.c, y.b)), mul(x.d, y.a));
-  return r;
-}
-__device__ __forceinline__ F4 tof4(uint4 w) { F4 r; r.a = w.x; r.b = w.y; r.c = w.z; r.d = w.w; return r; }
 // Lazy accumulation of sum_k pw_k * f_k (pw_k, f_k canonical): a 64-bit accumulator per Fp4 component takes one
 // IMAD.WIDE per term; after every second term its high word is brought back below P (one VIADDMNMX), which keeps the
 // accumulator below P * 2^32 + 2 P^2 < 2^64; a single Montgomery reduction at the end of the chain gives the canonical
 // word.  An accumulator that continues from a canonical value m starts as m << 32 (= m * R).
+__device__ __forceinline__ u64 wide(u32 f, u32 w) { return (u64)f * w; }
+__device__ __forceinline__ u64 widem(u32 m, u32 f, u32 w) { return ((u64)m << 32) + (u64)f * w; }
+__device__ __forceinline__ void wacc(u64& a, u32 f, u32 w) { a += (u64)f * w; }
 __device__ __forceinline__ u64 fixhi(u64 a) { u32 hi = (u32)(a >> 32); hi = min(hi, hi - P); return ((u64)hi << 32) | (u32)a; }
 __device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x88000001u; u32 r = (u32)(a >> 32) - __umulhi(m, P); return min(r, r + P); }
-__device__ __forceinline__ F4 scale4(F4 x, u32 s) { F4 r; r.a = mul(x.a, s); r.b = mul(x.b, s); r.c = mul(x.c, s); r.d = mul(x.d, s); return r; }
-__device__ __forceinline__ F4 add4(F4 x, F4 y) { F4 r; r.a = add(x.a, y.a); r.b = add(x.b, y.b); r.c = add(x.c, y.c); r.d = add(x.d, y.d); return r; }
+__device__ __forceinline__ void st(u32* p, u32 v) { *p = v; }
 )";
+
+// Several consecutive rows per thread (ROWS = 2 or 4): every tap is one 64 / 128-bit load, a tap `back` rows behind is a
+// neighbouring lane's vector (warp shuffle; only the first lanes of a warp load), and the per-row code is replicated
+// through overloads of the scalar helpers.  Values that do not depend on a tap (constants, globals) stay scalar.
+static std::string preamble_rows(int rows) {
+  const char* f[4] = {"x", "y", "z", "w"};
+  std::ostringstream o;
+  auto each = [&](const std::string& pat) {       // pat with '#' = field name, joined by spaces
+    std::string out;
+    for (int i = 0; i < rows; ++i) { std::string t = pat; size_t k; while ((k = t.find('#')) != std::string::npos) t.replace(k, 1, f[i]); out += t + " "; }
+    return out;
+  };
+  std::string fields; for (int i = 0; i < rows; ++i) fields += std::string(i ? ", " : "") + f[i];
+  o << "struct FV { u32 " << fields << "; };\nstruct AV { u64 " << fields << "; };\n";
+  for (const char* name : {"add", "sub", "mul"}) {
+    o << "__device__ __forceinline__ FV " << name << "(FV a, FV b) { FV r; " << each(std::string("r.# = ") + name + "(a.#, b.#);") << "return r; }\n";
+    o << "__device__ __forceinline__ FV " << name << "(FV a, u32 b) { FV r; " << each(std::string("r.# = ") + name + "(a.#, b);") << "return r; }\n";
+    o << "__device__ __forceinline__ FV " << name << "(u32 a, FV b) { FV r; " << each(std::string("r.# = ") + name + "(a, b.#);") << "return r; }\n";
+  }
+  o << "__device__ __forceinline__ AV wide(FV f, u32 w) { AV r; " << each("r.# = wide(f.#, w);") << "return r; }\n"
+    << "__device__ __forceinline__ AV widem(FV m, FV f, u32 w) { AV r; " << each("r.# = widem(m.#, f.#, w);") << "return r; }\n"
+    << "__device__ __forceinline__ AV widem(FV m, u32 f, u32 w) { AV r; " << each("r.# = widem(m.#, f, w);") << "return r; }\n"
+    << "__device__ __forceinline__ void wacc(AV& a, FV f, u32 w) { " << each("wacc(a.#, f.#, w);") << "}\n"
+    << "__device__ __forceinline__ void wacc(AV& a, u32 f, u32 w) { " << each("wacc(a.#, f, w);") << "}\n"
+    << "__device__ __forceinline__ AV fixhi(AV a) { AV r; " << each("r.# = fixhi(a.#);") << "return r; }\n"
+    << "__device__ __forceinline__ FV fin(AV a) { FV r; " << each("r.# = fin(a.#);") << "return r; }\n"
+    << "__device__ __forceinline__ AV W0(FV f, u32 w) { return wide(f, w); }\n"
+    << "__device__ __forceinline__ AV W0(u32 f, u32 w) { AV r; " << each("r.# = wide(f, w);") << "return r; }\n";
+  const char* vt = rows == 4 ? "uint4" : "uint2";
+  o << "__device__ __forceinline__ FV ldv(const u32* p) { const " << vt << " v = __ldg(reinterpret_cast<const " << vt << "*>(p)); FV r; " << each("r.# = v.#;") << "return r; }\n"
+    << "__device__ __forceinline__ void st(u32* p, FV v) { *reinterpret_cast<" << vt << "*>(p) = make_" << vt << "(" ;
+  for (int i = 0; i < rows; ++i) o << (i ? ", " : "") << "v." << f[i];
+  o << "); }\n"
+    // rows (c - 4 back ..) of a column: this thread's vector v0 of rows (c ..) moved up by 4 back / ROWS lanes; `p` = the direct address
+    << "__device__ __forceinline__ FV tap_shfl(FV v0, const u32* p, u32 lanes) {\n  FV r; " << each("r.# = __shfl_up_sync(0xffffffffu, v0.#, lanes);")
+    << "\n  if ((threadIdx.x & 31u) < lanes) r = ldv(p);\n  return r;\n}\n";
+  return o.str();
+}
+
+// Fp4 arithmetic over a component type T (u32: one row; FV: four rows); the second operand of mul4 is a power of poly_mix
+const char* PREAMBLE_F4 = R"(
+template <class T> struct F4T { T a, b, c, d; };
+typedef F4T<u32> F4;
+template <class T> __device__ __forceinline__ F4T<T> mul4(F4T<T> x, F4 y) {
+  F4T<T> r;
+  r.a = add(mul(x.a, y.a), mul(add(add(mul(x.b, y.d), mul(x.c, y.c)), mul(x.d, y.b)), NB));
+  r.b = add(add(mul(x.a, y.b), mul(x.b, y.a)), mul(add(mul(x.c, y.d), mul(x.d, y.c)), NB));
+  r.c = add(add(add(mul(x.a, y.c), mul(x.b, y.b)), mul(x.c, y.a)), mul(mul(x.d, y.d), NB));
+  r.d = add(add(add(mul(x.a, y.d), mul(x.b, y.c)), mul(x.c, y.b)), mul(x.d, y.a));
+  return r;
+}
+__device__ __forceinline__ F4 tof4(uint4 w) { F4 r; r.a = w.x; r.b = w.y; r.c = w.z; r.d = w.w; return r; }
+template <class T, class S> __device__ __forceinline__ F4T<T> scale4(F4T<T> x, S s) { F4T<T> r; r.a = mul(x.a, s); r.b = mul(x.b, s); r.c = mul(x.c, s); r.d = mul(x.d, s); return r; }
+template <class T> __device__ __forceinline__ F4T<T> add4(F4T<T> x, F4T<T> y) { F4T<T> r; r.a = add(x.a, y.a); r.b = add(x.b, y.b); r.c = add(x.c, y.c); r.d = add(x.d, y.d); return r; }
+)";
+
 
 uint64_t fnv1a(const std::string& s) {
   uint64_t h = 1469598103934665603ull;
@@ -133,17 +181,25 @@ struct EvalJitCache {
   std::map<uint64_t, bool> failed;
 };
 
-static int min_blocks();
-static uint32_t ec_batch() { const char* e = getenv("ZKB_EC_BATCH"); int v = e ? atoi(e) : 4; return (uint32_t)(v < 1 ? 1 : v > 4096 ? 4096 : v); }
+static int min_blocks(int rows);
+// rows per thread: 4 (vectorised) unless ZKB_EC_ROWS = 1
+// Measured on B200 (SYN-280, 2^22 domain points; profiles/r1_l_ec_variants.txt): one row per thread with indexed tap
+// addresses 2.5 ms; row pointers + uniform column offsets 2.7 ms; 2 rows per thread 3.7-4.1 ms; 4 rows per thread
+// 2.6-5.0 ms (the 16 64-bit accumulators spill) -- so ZKB_EC_ROWS = 1 and ZKB_EC_PTR = 0 are the defaults.
+static int ec_rows() { const char* e = getenv("ZKB_EC_ROWS"); int v = e ? atoi(e) : 1; return v == 2 || v == 4 ? v : 1; }
+static bool ec_ptr() { const char* e = getenv("ZKB_EC_PTR"); return e && atoi(e) != 0; }
+static uint32_t ec_batch(int rows) { const char* e = getenv("ZKB_EC_BATCH"); int v = e ? atoi(e) : (rows == 4 ? 1 : rows == 2 ? 2 : 4); return (uint32_t)(v < 1 ? 1 : v > 4096 ? 4096 : v); }
 static uint32_t ec_prefetch() { const char* e = getenv("ZKB_EC_PREFETCH"); int v = e ? atoi(e) : 1; return (uint32_t)(v < 0 ? 0 : v > 8 ? 8 : v); }
 // Per-proof kernel data: [powers of poly_mix, 4 words each][mix globals][out globals].  It lives in the module's
 // __constant__ bank when it fits (operands then come straight from the constant cache), else behind a pointer.
 constexpr size_t CONST_WORDS_MAX = 15 * 1024;
 static bool const_mode(const CircuitDef& c, uint32_t n_powers) { return 4 * (size_t)n_powers + c.mix_size + c.out_size <= CONST_WORDS_MAX; }
 
-// Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads.
-static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
+// Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads; rows = domain points per
+// thread (1, or 2 / 4 = vectorised form, see preamble_rows).
+static std::string generate(const CircuitDef& c, uint32_t& n_powers, int rows) {
   const size_t n = c.steps.size();
+  const bool vec = rows > 1;
   // liveness from the returned mix value backwards
   std::vector<char> fp_used(c.n_fp_vars, 0), mx_used(c.n_mix_vars, 0);
   std::vector<uint32_t> fp_of(n, 0), mx_of(n, 0);
@@ -177,6 +233,9 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
   const size_t gl_off = 4 * (size_t)n_powers;
   std::ostringstream o;
   o << PREAMBLE;
+  if (vec) o << preamble_rows(rows) << "typedef FV RV; typedef AV ACC;\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) ldv(p)\n";
+  else o << "typedef u32 RV; typedef u64 ACC;\n#define W0(f, w) wide(f, w)\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) __ldg(p)\n";
+  o << PREAMBLE_F4 << "typedef F4T<RV> MV;\n";
   if (cm) {
     o << "__constant__ u32 zkb_cd[" << std::max<size_t>(gl_off + c.mix_size + c.out_size, 4) << "];\n"
          "#define PW(k) make_uint4(zkb_cd[4 * (k)], zkb_cd[4 * (k) + 1], zkb_cd[4 * (k) + 2], zkb_cd[4 * (k) + 3])\n"
@@ -184,22 +243,37 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
   } else {
     o << "#define PW(k) __ldg(pw + (k))\n#define GL(i) __ldg(gl + (i))\n";
   }
-  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", " << min_blocks() << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
+  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", " << min_blocks(rows) << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
-       "  const u32 c = blockIdx.x * " << JIT_BLOCK << "u + threadIdx.x;\n  const size_t dom = (size_t)mask + 1;\n"
-       "#define TAP(g, col, back) __ldg(g + (size_t)(col) * dom + ((c - 4u * (back)) & mask))\n";
+       "  const size_t dom = (size_t)mask + 1;\n"
+       "  const u32 c = (blockIdx.x * " << JIT_BLOCK << "u + threadIdx.x) * " << rows << "u;\n";
+  // Tap addresses: one per-thread row pointer for every (group, back) pair in use, plus the CTA-uniform column offset
+  // col * dom -- the per-tap address arithmetic then runs on the uniform datapath / ALU instead of one IMAD.WIDE per load
+  // on the multiplier pipe (ZKB_EC_PTR=0 restores the indexed form).
+  const bool ptr_mode = ec_ptr();
+  if (ptr_mode) {
+    std::set<std::pair<uint32_t, uint32_t>> gb;
+    for (const TapDef& t : c.taps) gb.insert({t.group, t.back});
+    for (auto& e : gb) o << "  const u32* const rp" << e.first << "_" << e.second << " = g" << e.first << " + ((c - " << 4 * e.second << "u) & mask);\n";
+  }
+  auto tap_addr = [&](const TapDef& t) {
+    std::ostringstream a;
+    if (ptr_mode) a << "rp" << t.group << "_" << t.back << " + (size_t)" << t.column << " * dom";
+    else a << "g" << t.group << " + (size_t)" << t.column << " * dom + ((c - " << 4 * t.back << "u) & mask)";
+    return a.str();
+  };
   enum { ST_ZERO = 0, ST_CANON = 1, ST_ACC = 2 };
   std::vector<char> state(c.n_mix_vars, ST_ZERO);
   std::vector<uint32_t> acc_set(c.n_mix_vars, 0), acc_terms(c.n_mix_vars, 0);
-  auto materialize = [&](uint32_t id) {      // accumulators of `id` -> canonical F4 m<id>
+  auto materialize = [&](uint32_t id) {      // accumulators of `id` -> canonical Fp4 m<id>
     uint32_t a = acc_set[id];
-    o << "  F4 m" << id << "; m" << id << ".a = fin(A" << a << "_0); m" << id << ".b = fin(A" << a << "_1); m" << id << ".c = fin(A" << a << "_2); m" << id << ".d = fin(A" << a << "_3);\n";
+    o << "  MV m" << id << "; m" << id << ".a = fin(A" << a << "_0); m" << id << ".b = fin(A" << a << "_1); m" << id << ".c = fin(A" << a << "_2); m" << id << ".d = fin(A" << a << "_3);\n";
     state[id] = ST_CANON;
   };
   // Load scheduling.  The kernel is bound by global-load latency (ncu: 87 % long-scoreboard stalls when every tap is loaded
   // right before its use), so the tap loads of the next `batch` constraints are hoisted in front of the arithmetic of the
   // current ones (software pipelining, distance `prefetch` batches); a tap needed twice within the hoisted group is loaded once.
-  const uint32_t batch = ec_batch(), prefetch = ec_prefetch();
+  const uint32_t batch = ec_batch(rows), prefetch = ec_prefetch();
   std::vector<uint32_t> get_batch(n, 0);
   uint32_t n_batches = 1;
   {
@@ -217,14 +291,25 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
   std::vector<char> get_done(n, 0);
   auto hoist = [&](uint32_t b) {
     if (b >= gets_of.size()) return;
-    std::map<uint32_t, uint32_t> seen;       // tap -> fp id, within this group
-    for (size_t i : gets_of[b]) {
-      const StepDef& s = c.steps[i];
-      auto it = seen.find(s.a);
-      if (it != seen.end()) { o << "  const u32 f" << fp_of[i] << " = f" << it->second << ";\n"; }
-      else { const TapDef& t = c.taps[s.a]; o << "  const u32 f" << fp_of[i] << " = TAP(g" << t.group << ", " << t.column << ", " << t.back << ");\n"; seen[s.a] = fp_of[i]; }
-      get_done[i] = 1;
-    }
+    std::map<uint32_t, uint32_t> seen;                           // tap -> fp id, within this group
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> row0;      // (group, column) -> fp id of its back-0 tap, within this group
+    // back-0 taps first, so that a tap further back of the same column can take them from the neighbouring lanes
+    for (int pass = 0; pass < 2; ++pass)
+      for (size_t i : gets_of[b]) {
+        const StepDef& s = c.steps[i];
+        const TapDef& t = c.taps[s.a];
+        if ((t.back == 0) != (pass == 0)) continue;
+        auto it = seen.find(s.a);
+        if (it != seen.end()) { o << "  const RV f" << fp_of[i] << " = f" << it->second << ";\n"; }
+        else {
+          auto r0 = row0.find({t.group, t.column});
+          if (vec && t.back > 0 && 4 * t.back / rows < 32 && r0 != row0.end()) o << "  const RV f" << fp_of[i] << " = tap_shfl(f" << r0->second << ", " << tap_addr(t) << ", " << 4 * t.back / rows << "u);\n";
+          else o << "  const RV f" << fp_of[i] << " = LD(" << tap_addr(t) << ");\n";
+          seen[s.a] = fp_of[i];
+          if (t.back == 0) row0[{t.group, t.column}] = fp_of[i];
+        }
+        get_done[i] = 1;
+      }
   };
   uint32_t hoisted_upto = 0;                  // batches [0, hoisted_upto) have had their loads emitted
   auto hoist_until = [&](uint32_t b_end) { while (hoisted_upto < b_end && hoisted_upto < gets_of.size()) hoist(hoisted_upto++); };
@@ -237,10 +322,10 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
       uint32_t id = fi++;
       if (!fp_used[id]) continue;
       if (s.op == PX_GET && get_done[i]) continue;
-      o << "  const u32 f" << id << " = ";
+      o << "  const auto f" << id << " = ";
       switch (s.op) {
         case PX_CONST: o << Fp::from(s.a).v << "u"; break;
-        case PX_GET: { const TapDef& t = c.taps[s.a]; o << "TAP(g" << t.group << ", " << t.column << ", " << t.back << ")"; break; }
+        case PX_GET: o << "LD(" << tap_addr(c.taps[s.a]) << ")"; break;
         case PX_GET_GLOBAL: o << "GL(" << (s.a == 0 ? s.b : c.mix_size + s.b) << ")"; break;
         case PX_ADD: o << "add(f" << s.a << ", f" << s.b << ")"; break;
         case PX_SUB: o << "sub(f" << s.a << ", f" << s.b << ")"; break;
@@ -259,19 +344,19 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
       uint32_t set, terms;
       if (state[base] == ST_ACC && eqz_uses[base] == 1 && other_uses[base] == 0) {          // continue the chain in place
         set = acc_set[base]; terms = acc_terms[base];
-        o << "  { const uint4 w = PW(" << k << "); A" << set << "_0 += (u64)f" << s.b << " * w.x; A" << set << "_1 += (u64)f" << s.b << " * w.y; A" << set
-          << "_2 += (u64)f" << s.b << " * w.z; A" << set << "_3 += (u64)f" << s.b << " * w.w; }\n";
+        o << "  { const uint4 w = PW(" << k << "); wacc(A" << set << "_0, f" << s.b << ", w.x); wacc(A" << set << "_1, f" << s.b << ", w.y); wacc(A" << set
+          << "_2, f" << s.b << ", w.z); wacc(A" << set << "_3, f" << s.b << ", w.w); }\n";
         ++terms;
       } else {
         set = id;
         if (state[base] == ST_ACC) materialize(base);       // (cannot happen: multi-use values are materialised at definition)
         if (state[base] == ST_ZERO) {
-          o << "  u64 A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = (u64)f" << s.b
-            << " * w.x; A" << set << "_1 = (u64)f" << s.b << " * w.y; A" << set << "_2 = (u64)f" << s.b << " * w.z; A" << set << "_3 = (u64)f" << s.b << " * w.w; }\n";
+          o << "  ACC A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = W0(f" << s.b
+            << ", w.x); A" << set << "_1 = W0(f" << s.b << ", w.y); A" << set << "_2 = W0(f" << s.b << ", w.z); A" << set << "_3 = W0(f" << s.b << ", w.w); }\n";
         } else {
-          o << "  u64 A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = ((u64)m" << base
-            << ".a << 32) + (u64)f" << s.b << " * w.x; A" << set << "_1 = ((u64)m" << base << ".b << 32) + (u64)f" << s.b << " * w.y; A" << set << "_2 = ((u64)m" << base
-            << ".c << 32) + (u64)f" << s.b << " * w.z; A" << set << "_3 = ((u64)m" << base << ".d << 32) + (u64)f" << s.b << " * w.w; }\n";
+          o << "  ACC A" << set << "_0, A" << set << "_1, A" << set << "_2, A" << set << "_3; { const uint4 w = PW(" << k << "); A" << set << "_0 = WM(m" << base
+            << ".a, f" << s.b << ", w.x); A" << set << "_1 = WM(m" << base << ".b, f" << s.b << ", w.y); A" << set << "_2 = WM(m" << base
+            << ".c, f" << s.b << ", w.z); A" << set << "_3 = WM(m" << base << ".d, f" << s.b << ", w.w); }\n";
         }
         terms = 1;
       }
@@ -286,19 +371,21 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers) {
     // PX_AND_COND: m_id = m_a + f_b * (m_c (x) poly_mix^pow(a)); operands are canonical (materialised at definition)
     if (state[s.c] == ST_ZERO) {           // inner chain is empty: nothing is added
       if (state[s.a] == ST_ZERO) state[id] = ST_ZERO;
-      else { o << "  const F4 m" << id << " = m" << s.a << ";\n"; state[id] = ST_CANON; }
+      else { o << "  const MV m" << id << " = m" << s.a << ";\n"; state[id] = ST_CANON; }
       continue;
     }
-    o << "  const F4 m" << id << " = ";
+    o << "  const MV m" << id << " = ";
     if (state[s.a] == ST_ZERO) o << "scale4(mul4(m" << s.c << ", tof4(PW(" << mx_pow[s.a] << "))), f" << s.b << ")";
     else o << "add4(m" << s.a << ", scale4(mul4(m" << s.c << ", tof4(PW(" << mx_pow[s.a] << "))), f" << s.b << "))";
     o << ";\n";
     state[id] = ST_CANON;
   }
-  o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
-  if (state[c.ret] == ST_ZERO) o << "  F4 r; r.a = r.b = r.c = r.d = 0;\n";
-  else o << "  const F4 r = scale4(m" << c.ret << ", den);\n";
-  o << "  check[c] = r.a; check[dom + c] = r.b; check[2 * dom + c] = r.c; check[3 * dom + c] = r.d;\n}\n";
+  if (rows == 4) o << "  FV den; den.x = invden.x; den.y = invden.y; den.z = invden.z; den.w = invden.w;     // rows c .. c + 3: c is a multiple of 4\n";
+  else if (rows == 2) o << "  FV den; den.x = (c & 2u) ? invden.z : invden.x; den.y = (c & 2u) ? invden.w : invden.y;     // rows c, c + 1: c is even\n";
+  else o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
+  if (state[c.ret] == ST_ZERO) o << "  MV r; r.a = r.b = r.c = r.d = sub(den, den);\n";
+  else o << "  const MV r = scale4(m" << c.ret << ", den);\n";
+  o << "  st(check + c, r.a); st(check + dom + c, r.b); st(check + 2 * dom + c, r.c); st(check + 3 * dom + c, r.d);\n}\n";
   return o.str();
 }
 
@@ -318,7 +405,7 @@ static std::string cache_dir() {
   }
   return "/tmp/zkb200-cache";
 }
-static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : v > 16 ? 16 : v; }
+static int min_blocks(int rows) { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : (rows == 4 ? 4 : rows == 2 ? 6 : 8); return v < 1 ? 1 : v > 16 ? 16 : v; }
 
 static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
   Api& a = api();
@@ -357,23 +444,25 @@ void eval_jit_free(zkb_ctx* ctx) {
 }
 
 // The generated source (for tests / inspection) -- no device needed.
-std::string eval_jit_source(const CircuitDef& c) { uint32_t np; return generate(c, np); }
+std::string eval_jit_source(const CircuitDef& c) { uint32_t np; return generate(c, np, ec_rows()); }
 // Compiles the source with NVRTC without loading it (CPU-only check that the generator emits valid CUDA).
 bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return false; }
   std::vector<char> cubin; uint32_t np;
-  return compile(generate(c, np), cubin, why);
+  // both forms: the vectorised kernel, and the one-row-per-thread kernel used for tiny domains / unaligned sub-buffers
+  if (ec_rows() > 1 && !compile(generate(c, np, ec_rows()), cubin, why)) return false;
+  return compile(generate(c, np, 1), cubin, why);
 }
 
-static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, std::string& why) {
+static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, int rows, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return nullptr; }
   if (!a.cu_ok) { why = a.cu_why; return nullptr; }
   if (!ctx->jit) ctx->jit = new EvalJitCache();
   EvalJitCache* cache = (EvalJitCache*)ctx->jit;
   uint32_t np = 1;
-  std::string src = generate(c, np);
+  std::string src = generate(c, np, rows);
   uint64_t key = fnv1a(src);
   auto it = cache->kernels.find(key);
   if (it != cache->kernels.end()) return &it->second;
@@ -395,10 +484,14 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, std::s
 // Returns false (with `why`) when the JIT path is unavailable; the caller then uses the interpreter.
 bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint32_t* const d_groups[3], const uint32_t* mix_g, const uint32_t* out_g,
                     const Fp4& poly_mix, int po2, std::string& why) {
-  const EvalJitKernel* k = get_kernel(ctx, c, why);
-  if (!k) return false;
   const size_t n = (size_t)1 << po2, domain = n * INV_RATE;
   if (domain < (size_t)JIT_BLOCK) { why = "domain smaller than one block"; return false; }
+  // four rows per thread need 128-bit aligned columns (always true for pool allocations; a caller's sub-buffer view may not be)
+  int rows = ec_rows();
+  if (domain < (size_t)JIT_BLOCK * rows || ((uintptr_t)d_check & 15)) rows = 1;
+  for (int g = 0; g < 3; ++g) if ((uintptr_t)d_groups[g] & 15) rows = 1;
+  const EvalJitKernel* k = get_kernel(ctx, c, rows, why);
+  if (!k) return false;
   // per-proof data: [powers of poly_mix (4 words each)] [mix globals] [out globals]
   std::vector<uint32_t> h(4 * (size_t)k->n_powers + c.mix_size + c.out_size + 4);
   Fp4 cur = Fp4::one();
@@ -425,7 +518,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   const uint4* pw = (const uint4*)d_data; const uint32_t* d_gl = d_data + 4 * (size_t)k->n_powers;
   uint32_t mask = (uint32_t)(domain - 1);
   void* args[] = {&d_check, &g0, &g1, &g2, &pw, &d_gl, &invden, &mask};
-  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / JIT_BLOCK), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / ((size_t)JIT_BLOCK * rows)), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
   if (d_data) pool_free(ctx, d_data);

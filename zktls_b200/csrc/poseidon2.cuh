@@ -77,13 +77,17 @@ ZKB_HD void m_ext(uint32_t* s) {
   for (int i = 0; i < 24; ++i) s[i] = add_mod(s[i], sums[i & 3]);
 }
 
+// `z` is a zero the compiler cannot see through (the kernels pass a launch argument).  ptxas turns about a quarter of the
+// plain two-input additions into IMAD.IADD, i.e. onto the multiplier pipe the s-boxes saturate; writing the additions next
+// to the s-boxes and in the partial rounds as a + b + z keeps them 3-input IADD3s on the ALU pipe (+1.2 % permutations/s;
+// doing the same inside the external linear layer overloads the ALU pipe instead: -4 %, tools/ubench/p2_alu_adds.cu).
 template <typename Tables>
-ZKB_HD void permute(uint32_t* s, const Tables& T) {
+ZKB_HD void permute(uint32_t* s, const Tables& T, const uint32_t z = 0u) {
   m_ext(s);
 #pragma unroll 1
   for (int r = 0; r < 4; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox7(add_mod(s[i], T.ext[r * 24 + i]));
+    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(s[i] + T.ext[r * 24 + i] + z));
     m_ext(s);
   }
   // Partial rounds.  Cells are kept LAZY (in [0, 2P)) across these rounds: only cell 0 is made canonical for its
@@ -91,17 +95,17 @@ ZKB_HD void permute(uint32_t* s, const Tables& T) {
   // once to [0, P) -- so tot + product < 2P again with no second correction.
 #pragma unroll 1
   for (int r = 0; r < 21; ++r) {
-    s[0] = sbox7(add_mod(reduce_2p(s[0]), T.in[r]));
-    uint32_t tot = add_mod(sum12(s), sum12(s + 12));
+    s[0] = sbox7(reduce_2p(reduce_2p(s[0]) + T.in[r] + z));
+    uint32_t tot = reduce_2p(sum12(s) + sum12(s + 12) + z);
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = tot + reduce_2p(shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i]));
+    for (int i = 0; i < 24; ++i) s[i] = tot + reduce_2p(shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])) + z;
   }
 #pragma unroll
   for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
 #pragma unroll 1
   for (int r = 4; r < 8; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox7(add_mod(s[i], T.ext[r * 24 + i]));
+    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(s[i] + T.ext[r * 24 + i] + z));
     m_ext(s);
   }
 }
