@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=2, help="segments proven concurrently per GPU (one host thread + stream each)")
     ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
+    ap.add_argument("--session-segments", type=int, default=64, help="segments of the synthetic TLS session timed for the 'e2e TLS prove s' metric (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -306,6 +307,24 @@ def main():
     e2e_value = world * args.steps / (float(t.item()) / 1000.0)
     assert np.array_equal(seal, seal_h), "device-resident and host-buffer paths disagree"
 
+    # ---- BASELINE metric "e2e TLS prove s": one TLS session = S continuation segments (S = 64 for a
+    # 64 KB AES-128-GCM response), segment i -> rank i mod N, every segment uploaded from pinned host memory and its seal read back
+    session = None
+    if args.session_segments > 0:
+        from zktls_b200.shard import segments_for_rank
+        mine = len(segments_for_rank(args.session_segments, rank, world))
+        first_up = [threading.Event() for _ in range(inflight)]
+        barrier()
+        hal.timer_start(); ts0 = time.time()
+        run_workers(host_worker, mine)
+        ms_sess = hal.timer_stop()
+        barrier()
+        t = torch.tensor([ms_sess], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        session = {"segments": args.session_segments, "seconds": float(t.item()) / 1000.0, "wall_s_rank0": time.time() - ts0,
+                   "what": "synthetic stand-in for one recorded TLS session: S independent SYN-280 2^20-cycle segments, segment-parallel over the ranks, host traces in / seals out"}
+
     # ---- roofline of the dominant kernel (hash_rows over the data group's LDE matrix), live CUDA events -----------------
     roof = None
     if rank == 0:
@@ -373,7 +392,7 @@ def main():
                 "config": dict(workload_config(), segments_in_flight_per_gpu=inflight), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k"},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
+                "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if po2 != PO2:
             line["config"]["workload"] = f"DEBUG po2={po2} (not the benchmark config)"
         print(json.dumps(line), flush=True)

@@ -48,6 +48,7 @@ struct Api {
   CUresult (*getErrorString)(CUresult, const char**);
   CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
   CUresult (*memcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream);
+  CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int);
 };
 
 Api& api() {
@@ -77,6 +78,7 @@ Api& api() {
     a.getErrorString = (decltype(a.getErrorString))sym(cu, "cuGetErrorString");
     a.moduleGetGlobal = (decltype(a.moduleGetGlobal))sym(cu, "cuModuleGetGlobal_v2");
     a.memcpyHtoDAsync = (decltype(a.memcpyHtoDAsync))sym(cu, "cuMemcpyHtoDAsync_v2");
+    a.funcSetAttribute = (decltype(a.funcSetAttribute))sym(cu, "cuFuncSetAttribute");
     a.cu_ok = all;
     if (!all) a.cu_why = a.why;
   });
@@ -173,6 +175,8 @@ struct EvalJitKernel {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   uint32_t n_powers = 1;
+  int rows = 1, block = 128;      // domain points per thread, threads per CTA
+  size_t smem = 0;                // dynamic shared memory per CTA
   CUdeviceptr cdata = 0;        // __constant__ zkb_cd (per-proof powers + globals) when the circuit's data fits in 64 KB
   size_t cdata_bytes = 0;
 };
@@ -197,42 +201,137 @@ static bool const_mode(const CircuitDef& c, uint32_t n_powers) { return 4 * (siz
 
 // Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads; rows = domain points per
 // thread (1, or 2 / 4 = vectorised form, see preamble_rows).
-static std::string generate(const CircuitDef& c, uint32_t& n_powers, int rows) {
+// Liveness and mix-power bookkeeping shared by the generators.
+struct Analysis {
+  std::vector<char> fp_used, mx_used;
+  std::vector<uint32_t> fp_of, mx_of;             // step index -> fp / mix value id
+  std::vector<uint32_t> eqz_uses, other_uses;     // how each live mix value is consumed: as the base of a following AndEqz (chainable), or otherwise
+  std::vector<uint32_t> mx_pow;                   // power of poly_mix a mix value has reached
+  uint32_t n_powers = 1;
+};
+static Analysis analyse(const CircuitDef& c) {
+  Analysis A;
   const size_t n = c.steps.size();
-  const bool vec = rows > 1;
-  // liveness from the returned mix value backwards
-  std::vector<char> fp_used(c.n_fp_vars, 0), mx_used(c.n_mix_vars, 0);
-  std::vector<uint32_t> fp_of(n, 0), mx_of(n, 0);
-  { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) fp_of[i] = fi++; else mx_of[i] = mi++; } }
-  mx_used[c.ret] = 1;
-  for (size_t i = n; i-- > 0;) {
+  A.fp_used.assign(c.n_fp_vars, 0); A.mx_used.assign(c.n_mix_vars, 0);
+  A.fp_of.assign(n, 0); A.mx_of.assign(n, 0);
+  { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) A.fp_of[i] = fi++; else A.mx_of[i] = mi++; } }
+  A.mx_used[c.ret] = 1;
+  for (size_t i = n; i-- > 0;) {      // liveness from the returned mix value backwards
     const StepDef& s = c.steps[i];
     switch (s.op) {
-      case PX_ADD: case PX_SUB: case PX_MUL: if (fp_used[fp_of[i]]) fp_used[s.a] = fp_used[s.b] = 1; break;
-      case PX_AND_EQZ: if (mx_used[mx_of[i]]) { mx_used[s.a] = 1; fp_used[s.b] = 1; } break;
-      case PX_AND_COND: if (mx_used[mx_of[i]]) { mx_used[s.a] = mx_used[s.c] = 1; fp_used[s.b] = 1; } break;
+      case PX_ADD: case PX_SUB: case PX_MUL: if (A.fp_used[A.fp_of[i]]) A.fp_used[s.a] = A.fp_used[s.b] = 1; break;
+      case PX_AND_EQZ: if (A.mx_used[A.mx_of[i]]) { A.mx_used[s.a] = 1; A.fp_used[s.b] = 1; } break;
+      case PX_AND_COND: if (A.mx_used[A.mx_of[i]]) { A.mx_used[s.a] = A.mx_used[s.c] = 1; A.fp_used[s.b] = 1; } break;
       default: break;
     }
   }
-  // how each live mix value is consumed: as the base of a following AndEqz (chainable), or otherwise (needs a canonical F4)
-  std::vector<uint32_t> eqz_uses(c.n_mix_vars, 0), other_uses(c.n_mix_vars, 0);
-  std::vector<uint32_t> mx_pow(c.n_mix_vars, 0);
-  n_powers = 1;
-  {
-    uint32_t mi = 0;
-    for (size_t i = 0; i < n; ++i) {
-      const StepDef& s = c.steps[i];
-      if (s.op <= PX_MUL) continue;
-      uint32_t id = mi++;
-      if (s.op == PX_AND_EQZ) { mx_pow[id] = mx_pow[s.a] + 1; if (mx_used[id]) { ++eqz_uses[s.a]; n_powers = std::max(n_powers, mx_pow[s.a] + 1); } }
-      else if (s.op == PX_AND_COND) { mx_pow[id] = mx_pow[s.a] + mx_pow[s.c]; if (mx_used[id]) { ++other_uses[s.a]; ++other_uses[s.c]; n_powers = std::max(n_powers, mx_pow[s.a] + 1); } }
-    }
-    ++other_uses[c.ret];
+  A.eqz_uses.assign(c.n_mix_vars, 0); A.other_uses.assign(c.n_mix_vars, 0); A.mx_pow.assign(c.n_mix_vars, 0);
+  uint32_t mi = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const StepDef& s = c.steps[i];
+    if (s.op <= PX_MUL) continue;
+    uint32_t id = mi++;
+    if (s.op == PX_AND_EQZ) { A.mx_pow[id] = A.mx_pow[s.a] + 1; if (A.mx_used[id]) { ++A.eqz_uses[s.a]; A.n_powers = std::max(A.n_powers, A.mx_pow[s.a] + 1); } }
+    else if (s.op == PX_AND_COND) { A.mx_pow[id] = A.mx_pow[s.a] + A.mx_pow[s.c]; if (A.mx_used[id]) { ++A.other_uses[s.a]; ++A.other_uses[s.c]; A.n_powers = std::max(A.n_powers, A.mx_pow[s.a] + 1); } }
   }
+  ++A.other_uses[c.ret];
+  return A;
+}
+
+// Shared-memory staged form (mode "staged"): a CTA owns SG_BLOCK consecutive domain points.  The columns its constraints
+// read are brought into shared memory by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) issued by one
+// elected thread: columns read many times (the code group's constants) stay resident, the others stream through a ring of
+// `stages` slots of `cps` columns, refilled `stages` blocks ahead of their use.  Taps then are LDS with an immediate offset
+// (row - 4 back is the same column slot, a few words earlier: the slot holds `halo` rows in front of the tile), the loads
+// in flight per SM are decoupled from the register file (ring bytes instead of registers), and no address arithmetic runs
+// on the multiplier pipe.
+constexpr int SG_BLOCK = 256;
+struct GenInfo {
+  uint32_t n_powers = 1;
+  int rows = 1;              // domain points per thread
+  int block = JIT_BLOCK;     // threads per CTA
+  size_t smem = 0;           // dynamic shared memory (staged form)
+  bool staged = false;
+};
+static bool ec_staged() { const char* e = getenv("ZKB_EC_STAGED"); return !e || atoi(e) != 0; }
+static uint32_t env_u32(const char* name, uint32_t def, uint32_t lo, uint32_t hi) { const char* e = getenv(name); long v = e ? atol(e) : (long)def; return (uint32_t)(v < (long)lo ? lo : v > (long)hi ? hi : v); }
+
+const char* PREAMBLE_STAGED = R"(
+__device__ __forceinline__ u32 saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(saddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(saddr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  u32 ok;
+  do { asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(saddr(bar)), "r"(parity) : "memory"); } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(u32* dst, const u32* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+// rows [c0 - HALO, c0 + BLOCK) of one column into a slot; the first tile wraps around the end of the domain
+__device__ __forceinline__ void copy_col(u32* dst, const u32* col, u32 c0, u32 mask, u64* bar) {
+  if (HALO == 0) bulk_g2s(dst, col + c0, BLOCK * 4u, bar);
+  else if (c0 >= HALO) bulk_g2s(dst, col + (c0 - HALO), ROWP * 4u, bar);
+  else { bulk_g2s(dst, col + ((c0 - HALO) & mask), HALO * 4u, bar); bulk_g2s(dst + HALO, col + c0, BLOCK * 4u, bar); }
+}
+)";
+
+static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool staged) {
+  const size_t n = c.steps.size();
+  if (staged) rows = 1;
+  const bool vec = rows > 1;
+  const Analysis A = analyse(c);
+  uint32_t& n_powers = gi.n_powers;
+  gi.rows = rows; gi.block = JIT_BLOCK; gi.smem = 0; gi.staged = false;
+  const std::vector<char>&fp_used = A.fp_used, &mx_used = A.mx_used;
+  const std::vector<uint32_t>&fp_of = A.fp_of, &eqz_uses = A.eqz_uses, &other_uses = A.other_uses, &mx_pow = A.mx_pow;
+  n_powers = A.n_powers;
   const bool cm = const_mode(c, n_powers);
   const size_t gl_off = 4 * (size_t)n_powers;
+  // ---- staged form: which columns are resident, which stream, and in which block / slot every tap is found ----------
+  struct ColUse { uint32_t group, column, uses; };
+  uint32_t halo = 0, n_res = 0, cps = 0, stages = 0, rowp = 0;
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> res_slot;               // resident (group, column) -> slot
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> blocks;           // streamed columns of every block, slot order
+  std::vector<uint32_t> get_block(n, 0), get_slot(n, 0);
+  if (staged) {
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> uses;
+    for (size_t i = 0; i < n; ++i) if (c.steps[i].op == PX_GET && fp_used[fp_of[i]]) {
+      const TapDef& t = c.taps[c.steps[i].a];
+      ++uses[{t.group, t.column}];
+      halo = std::max(halo, 4 * t.back);
+    }
+    const uint32_t res_max = env_u32("ZKB_EC_RES", 32, 0, 64), res_min_uses = env_u32("ZKB_EC_RES_USES", 4, 2, 1u << 30);
+    // measured on B200, SYN-280 (profiles/r1_o_ec_staged.txt): 3 stages x 6 columns = 1.89 ms (34 KB per CTA, six CTAs per SM); deeper or
+    // wider rings cost occupancy (6 x 8: 3.25 ms, 10 x 8: 4.35 ms), the register form above takes 2.51 ms
+    cps = env_u32("ZKB_EC_CPS", 6, 1, 32); stages = env_u32("ZKB_EC_STAGES", 3, 2, 16);
+    std::vector<ColUse> cand;
+    for (auto& kv : uses) if (kv.second >= res_min_uses) cand.push_back({kv.first.first, kv.first.second, kv.second});
+    std::stable_sort(cand.begin(), cand.end(), [](const ColUse& x, const ColUse& y) { return x.uses > y.uses; });
+    for (auto& cu : cand) { if (n_res >= res_max) break; res_slot[{cu.group, cu.column}] = n_res++; }
+    rowp = SG_BLOCK + halo;
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> cur;                  // streamed column -> slot in the block being formed
+    blocks.emplace_back();
+    for (size_t i = 0; i < n; ++i) if (c.steps[i].op == PX_GET && fp_used[fp_of[i]]) {
+      const TapDef& t = c.taps[c.steps[i].a];
+      std::pair<uint32_t, uint32_t> key{t.group, t.column};
+      if (res_slot.count(key)) { get_block[i] = (uint32_t)blocks.size() - 1; continue; }
+      auto it = cur.find(key);
+      if (it == cur.end()) {
+        if (cur.size() == cps) { blocks.emplace_back(); cur.clear(); }
+        it = cur.emplace(key, (uint32_t)cur.size()).first;
+        blocks.back().push_back(key);
+      }
+      get_block[i] = (uint32_t)blocks.size() - 1; get_slot[i] = it->second;
+    }
+    if (blocks.back().empty() && blocks.size() > 1) blocks.pop_back();
+    stages = std::min<uint32_t>(stages, (uint32_t)std::max<size_t>(blocks.size(), 1));
+    gi.smem = ((size_t)n_res + (size_t)stages * cps) * rowp * 4 + (stages + 1) * 8;
+    if (halo > SG_BLOCK || gi.smem > 200 * 1024) return std::string();      // does not fit this form: the caller uses the register form
+    gi.block = SG_BLOCK; gi.staged = true;
+  }
   std::ostringstream o;
   o << PREAMBLE;
+  if (staged) o << "#define HALO " << halo << "u\n#define BLOCK " << SG_BLOCK << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
   if (vec) o << preamble_rows(rows) << "typedef FV RV; typedef AV ACC;\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) ldv(p)\n";
   else o << "typedef u32 RV; typedef u64 ACC;\n#define W0(f, w) wide(f, w)\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) __ldg(p)\n";
   o << PREAMBLE_F4 << "typedef F4T<RV> MV;\n";
@@ -243,10 +342,59 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers, int rows) {
   } else {
     o << "#define PW(k) __ldg(pw + (k))\n#define GL(i) __ldg(gl + (i))\n";
   }
-  o << "extern \"C\" __global__ void __launch_bounds__(" << JIT_BLOCK << ", " << min_blocks(rows) << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
+  const int ctas_per_sm = staged ? (int)std::max<size_t>(1, std::min<size_t>(env_u32("ZKB_EC_MINBLOCKS", 8, 1, 16), (220 * 1024) / (gi.smem + 1024))) : min_blocks(rows);
+  o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", " << ctas_per_sm << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
-       "  const size_t dom = (size_t)mask + 1;\n"
-       "  const u32 c = (blockIdx.x * " << JIT_BLOCK << "u + threadIdx.x) * " << rows << "u;\n";
+       << (staged ? "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));     // opaque: see the note on uniform address arithmetic below\n"
+                  : "  const size_t dom = (size_t)mask + 1;\n")
+       << "  const u32 c = (blockIdx.x * " << gi.block << "u + threadIdx.x) * " << rows << "u;\n";
+  // producer code of one block: expect the bytes, then one bulk copy per column (issued by thread 0 only)
+  auto issue_block = [&](uint32_t b) {
+    const uint32_t st = b % stages;
+    o << "    mbar_expect_tx(full + " << st << ", " << blocks[b].size() * rowp * 4 << "u);\n";
+    for (size_t k = 0; k < blocks[b].size(); ++k)
+      o << "    copy_col(ring + " << ((size_t)st * cps + k) * rowp << "u, g" << blocks[b][k].first << " + (size_t)" << blocks[b][k].second << " * dom, c0, mask, full + " << st << ");\n";
+  };
+  uint32_t cur_block = 0;
+  if (staged) {
+    o << "  extern __shared__ __align__(128) u32 zkb_sm[];\n"
+         "  u32* const ring = zkb_sm + " << (size_t)n_res * rowp << "u;\n"
+         "  u64* const full = reinterpret_cast<u64*>(zkb_sm + " << ((size_t)n_res + (size_t)stages * cps) * rowp << "u);     // [stages] ring barriers + 1 for the resident columns\n"
+         "  const u32 c0 = blockIdx.x * BLOCK;\n"
+         "  const u32* const sp = zkb_sm + threadIdx.x + HALO;          // this thread's row inside every column slot\n"
+         "  if (threadIdx.x == 0) {\n    for (u32 i = 0; i <= " << stages << "u; ++i) mbar_init(full + i, 1u);\n"
+         "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n  }\n  __syncthreads();\n"
+         "  if (threadIdx.x == 0) {\n";
+    if (n_res) {
+      o << "    mbar_expect_tx(full + " << stages << ", " << (size_t)n_res * rowp * 4 << "u);\n";
+      for (auto& kv : res_slot) o << "    copy_col(zkb_sm + " << (size_t)kv.second * rowp << "u, g" << kv.first.first << " + (size_t)" << kv.first.second << " * dom, c0, mask, full + " << stages << ");\n";
+    }
+    for (uint32_t b = 0; b < stages && b < blocks.size(); ++b) if (!blocks[b].empty()) issue_block(b);
+    o << "  }\n";
+    if (n_res) o << "  mbar_wait(full + " << stages << ", 0u);\n";
+    if (!blocks[0].empty()) o << "  mbar_wait(full + 0, 0u);\n";
+  }
+  // moves the kernel from block `cur_block` to block b: everybody has finished reading the old slot before it is refilled
+  auto advance_to = [&](uint32_t b) {
+    while (cur_block < b) {
+      if (cur_block + stages < blocks.size()) {
+        o << "  __syncthreads();\n  if (threadIdx.x == 0) {\n    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
+        issue_block(cur_block + stages);
+        o << "  }\n";
+      }
+      ++cur_block;
+      o << "  mbar_wait(full + " << cur_block % stages << ", " << ((cur_block / stages) & 1) << "u);\n";
+    }
+  };
+  auto staged_get = [&](size_t i) {
+    const TapDef& t = c.taps[c.steps[i].a];
+    advance_to(get_block[i]);
+    auto r = res_slot.find({t.group, t.column});
+    std::ostringstream a;
+    const long slot_words = r != res_slot.end() ? (long)r->second * rowp : (long)((size_t)n_res + (size_t)(get_block[i] % stages) * cps + get_slot[i]) * rowp;
+    a << "sp[" << slot_words - 4 * (long)t.back << "]";
+    return a.str();
+  };
   // Tap addresses: one per-thread row pointer for every (group, back) pair in use, plus the CTA-uniform column offset
   // col * dom -- the per-tap address arithmetic then runs on the uniform datapath / ALU instead of one IMAD.WIDE per load
   // on the multiplier pipe (ZKB_EC_PTR=0 restores the indexed form).
@@ -287,7 +435,7 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers, int rows) {
     n_batches = live_mix / batch + 1;
   }
   std::vector<std::vector<size_t>> gets_of(n_batches + 1);
-  for (size_t i = 0; i < n; ++i) if (c.steps[i].op == PX_GET && fp_used[fp_of[i]]) gets_of[std::min<uint32_t>(get_batch[i], n_batches)].push_back(i);
+  if (!staged) for (size_t i = 0; i < n; ++i) if (c.steps[i].op == PX_GET && fp_used[fp_of[i]]) gets_of[std::min<uint32_t>(get_batch[i], n_batches)].push_back(i);
   std::vector<char> get_done(n, 0);
   auto hoist = [&](uint32_t b) {
     if (b >= gets_of.size()) return;
@@ -322,10 +470,12 @@ static std::string generate(const CircuitDef& c, uint32_t& n_powers, int rows) {
       uint32_t id = fi++;
       if (!fp_used[id]) continue;
       if (s.op == PX_GET && get_done[i]) continue;
+      std::string get_expr;
+      if (s.op == PX_GET) get_expr = staged ? staged_get(i) : "LD(" + tap_addr(c.taps[s.a]) + ")";      // (staged_get may first emit a block change)
       o << "  const auto f" << id << " = ";
       switch (s.op) {
         case PX_CONST: o << Fp::from(s.a).v << "u"; break;
-        case PX_GET: o << "LD(" << tap_addr(c.taps[s.a]) << ")"; break;
+        case PX_GET: o << get_expr; break;
         case PX_GET_GLOBAL: o << "GL(" << (s.a == 0 ? s.b : c.mix_size + s.b) << ")"; break;
         case PX_ADD: o << "add(f" << s.a << ", f" << s.b << ")"; break;
         case PX_SUB: o << "sub(f" << s.a << ", f" << s.b << ")"; break;
@@ -444,35 +594,43 @@ void eval_jit_free(zkb_ctx* ctx) {
 }
 
 // The generated source (for tests / inspection) -- no device needed.
-std::string eval_jit_source(const CircuitDef& c) { uint32_t np; return generate(c, np, ec_rows()); }
+std::string eval_jit_source(const CircuitDef& c) {
+  GenInfo gi;
+  if (ec_staged()) { std::string src = generate(c, gi, 1, true); if (!src.empty()) return src; }
+  return generate(c, gi, ec_rows(), false);
+}
 // Compiles the source with NVRTC without loading it (CPU-only check that the generator emits valid CUDA).
 bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return false; }
-  std::vector<char> cubin; uint32_t np;
-  // both forms: the vectorised kernel, and the one-row-per-thread kernel used for tiny domains / unaligned sub-buffers
-  if (ec_rows() > 1 && !compile(generate(c, np, ec_rows()), cubin, why)) return false;
-  return compile(generate(c, np, 1), cubin, why);
+  std::vector<char> cubin; GenInfo gi;
+  // every form a proof may use: the staged kernel, and the register form used for tiny domains / unaligned sub-buffers
+  if (ec_staged()) { std::string src = generate(c, gi, 1, true); if (!src.empty() && !compile(src, cubin, why)) return false; }
+  if (ec_rows() > 1 && !compile(generate(c, gi, ec_rows(), false), cubin, why)) return false;
+  return compile(generate(c, gi, 1, false), cubin, why);
 }
 
-static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, int rows, std::string& why) {
+static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, int rows, bool staged, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return nullptr; }
   if (!a.cu_ok) { why = a.cu_why; return nullptr; }
   if (!ctx->jit) ctx->jit = new EvalJitCache();
   EvalJitCache* cache = (EvalJitCache*)ctx->jit;
-  uint32_t np = 1;
-  std::string src = generate(c, np, rows);
+  GenInfo gi;
+  std::string src = generate(c, gi, rows, staged);
+  if (src.empty()) { why = "circuit does not fit the staged form"; return nullptr; }
+  const uint32_t np = gi.n_powers;
   uint64_t key = fnv1a(src);
   auto it = cache->kernels.find(key);
   if (it != cache->kernels.end()) return &it->second;
   if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return nullptr; }
   std::vector<char> cubin;
-  EvalJitKernel k; k.n_powers = np;
+  EvalJitKernel k; k.n_powers = np; k.rows = gi.rows; k.block = gi.block; k.smem = gi.smem;
   if (!compile(src, cubin, why)) { cache->failed[key] = true; return nullptr; }
   ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
   if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
+  if (r == CUDA_SUCCESS && k.smem > 48 * 1024) r = a.funcSetAttribute(k.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k.smem);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleLoadData: ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
   if (const_mode(c, np)) {
     r = a.moduleGetGlobal(&k.cdata, &k.cdata_bytes, k.mod, "zkb_cd");
@@ -488,10 +646,17 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   if (domain < (size_t)JIT_BLOCK) { why = "domain smaller than one block"; return false; }
   // four rows per thread need 128-bit aligned columns (always true for pool allocations; a caller's sub-buffer view may not be)
   int rows = ec_rows();
-  if (domain < (size_t)JIT_BLOCK * rows || ((uintptr_t)d_check & 15)) rows = 1;
-  for (int g = 0; g < 3; ++g) if ((uintptr_t)d_groups[g] & 15) rows = 1;
-  const EvalJitKernel* k = get_kernel(ctx, c, rows, why);
+  bool aligned = ((uintptr_t)d_check & 15) == 0;
+  for (int g = 0; g < 3; ++g) if ((uintptr_t)d_groups[g] & 15) aligned = false;
+  if (domain < (size_t)JIT_BLOCK * rows || !aligned) rows = 1;
+  const EvalJitKernel* k = nullptr;
+  if (ec_staged() && aligned && domain >= (size_t)SG_BLOCK) {       // bulk copies need 16-byte aligned columns
+    std::string why_staged;
+    k = get_kernel(ctx, c, 1, true, why_staged);
+  }
+  if (!k) k = get_kernel(ctx, c, rows, false, why);
   if (!k) return false;
+  rows = k->rows;
   // per-proof data: [powers of poly_mix (4 words each)] [mix globals] [out globals]
   std::vector<uint32_t> h(4 * (size_t)k->n_powers + c.mix_size + c.out_size + 4);
   Fp4 cur = Fp4::one();
@@ -518,7 +683,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   const uint4* pw = (const uint4*)d_data; const uint32_t* d_gl = d_data + 4 * (size_t)k->n_powers;
   uint32_t mask = (uint32_t)(domain - 1);
   void* args[] = {&d_check, &g0, &g1, &g2, &pw, &d_gl, &invden, &mask};
-  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / ((size_t)JIT_BLOCK * rows)), 1, 1, JIT_BLOCK, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / ((size_t)k->block * rows)), 1, 1, (unsigned)k->block, 1, 1, (unsigned)k->smem, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
   if (d_data) pool_free(ctx, d_data);
