@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
     ap.add_argument("--cpu-sample-po2", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="segments proven concurrently per GPU (one host thread + stream each)")
+    ap.add_argument("--inflight", type=int, default=3, help="segments proven concurrently per GPU (one host thread + stream each)")
     ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
     ap.add_argument("--session-segments", type=int, default=64, help="segments of the synthetic TLS session timed for the 'e2e TLS prove s' metric (0 = skip)")
     args = ap.parse_args()

@@ -15,7 +15,27 @@ using namespace zkb;
 template <int Z> __device__ __forceinline__ uint32_t addz(uint32_t a, uint32_t b, uint32_t z) { return Z ? a + b + z : a + b; }
 template <int Z> __device__ __forceinline__ uint32_t addm(uint32_t a, uint32_t b, uint32_t z) { return reduce_2p(addz<Z>(a, b, z)); }
 template <int C> __device__ __forceinline__ uint32_t mmc(uint32_t a, uint32_t b) { return C ? reduce_2p(mont_mul_lazy(a, b)) : mont_mul(a, b); }
+// bit4..: Montgomery factor m = lo * P^-1 with P^-1 = 2^31 + 2^27 + 1 as two shift-adds (LEA, ALU pipe) instead of one IMAD
+// (fmaheavy pipe, measured 90 % busy in k_hash_rows).  NM = how many of the four products of an s-box use it.
+__device__ __forceinline__ uint32_t m_alu(uint32_t lo) { uint32_t t = (lo << 27) + lo; return (lo << 31) + t; }
+template <int ALUM> __device__ __forceinline__ uint32_t mm_lazy(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = ALUM ? m_alu((uint32_t)t) : (uint32_t)t * P_INV;
+  return (uint32_t)(t >> 32) - mul_hi32(m, P) + P;
+}
+template <int ALUM> __device__ __forceinline__ uint32_t mm_canon(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = ALUM ? m_alu((uint32_t)t) : (uint32_t)t * P_INV;
+  uint32_t r = (uint32_t)(t >> 32) - mul_hi32(m, P);
+  uint32_t y = r + P;
+  return y < r ? y : r;
+}
+template <int NM> __device__ __forceinline__ uint32_t sbox_m(uint32_t x) {
+  uint32_t x2 = mm_canon<(NM >= 1)>(x, x), x4 = mm_lazy<(NM >= 2)>(x2, x2), x6 = mm_lazy<(NM >= 3)>(x4, x2);
+  return mm_canon<(NM >= 4)>(x6, x);
+}
 template <int C> __device__ __forceinline__ uint32_t sbox(uint32_t x) {
+  if (C >= 16) return sbox_m<C / 16>(x);
   uint32_t x2 = mmc<C>(x, x), x4 = mont_mul_lazy(x2, x2), x6 = mont_mul_lazy(x4, x2);
   return mmc<C>(x6, x);
 }
@@ -39,7 +59,7 @@ template <int Z> __device__ __forceinline__ void mext(uint32_t* s, uint32_t z) {
   for (int i = 0; i < 24; ++i) s[i] = addm<Z>(s[i], sums[i & 3], z);
 }
 template <int V> __device__ __forceinline__ void permute_v(uint32_t* s, uint32_t z) {
-  constexpr int C = V & 1, Z1 = (V >> 1) & 1, Z2 = (V >> 2) & 1, Z3 = (V >> 3) & 1;
+  constexpr int C = (V >= 16) ? (V & ~15) : (V & 1), Z1 = (V >> 1) & 1, Z2 = (V >> 2) & 1, Z3 = (V >> 3) & 1;      // V >= 16: V / 16 = products per s-box with the ALU m
   const auto& T = ZKB_P2_TABLES;
   mext<Z2>(s, z);
 #pragma unroll 1
@@ -65,6 +85,70 @@ template <int V> __device__ __forceinline__ void permute_v(uint32_t* s, uint32_t
   }
 }
 
+// ---- second family: every chosen 2-input addition / subtraction written as min(a + b, ones) with `ones` = 0xffffffff held
+// in a uniform register (kernel argument).  ptxas fuses that into ONE VIADDMNMX.U32 Rd, Ra, +-Rb, URones -- an ALU-pipe
+// instruction -- and cannot turn it into IMAD.IADD.  W bits: 1 = the canonical products of the s-box (hi - u), 2 = round-constant
+// additions, 4 = external linear layer, 8 = partial rounds.
+template <int ON> __device__ __forceinline__ uint32_t addw(uint32_t a, uint32_t b, uint32_t ones) { return ON ? min(a + b, ones) : a + b; }
+template <int ON> __device__ __forceinline__ uint32_t subw(uint32_t a, uint32_t b, uint32_t ones) { return ON ? min(a - b, ones) : a - b; }
+template <int ON> __device__ __forceinline__ uint32_t addmw(uint32_t a, uint32_t b, uint32_t ones) { return reduce_2p(addw<ON>(a, b, ones)); }
+template <int ON> __device__ __forceinline__ uint32_t mmw(uint32_t a, uint32_t b, uint32_t ones) {      // canonical Montgomery product
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = (uint32_t)t * P_INV;
+  uint32_t r = subw<ON>((uint32_t)(t >> 32), mul_hi32(m, P), ones);
+  uint32_t y = r + P;
+  return y < r ? y : r;
+}
+template <int ON> __device__ __forceinline__ uint32_t sboxw(uint32_t x, uint32_t ones) {
+  uint32_t x2 = mmw<ON>(x, x, ones), x4 = mont_mul_lazy(x2, x2), x6 = mont_mul_lazy(x4, x2);
+  return mmw<ON>(x6, x, ones);
+}
+template <int ON> __device__ __forceinline__ void m4w(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t o) {
+  uint32_t t0 = addmw<ON>(x0, x1, o), t1 = addmw<ON>(x2, x3, o);
+  uint32_t t2 = addmw<ON>(addmw<ON>(x1, x1, o), t1, o), t3 = addmw<ON>(addmw<ON>(x3, x3, o), t0, o);
+  uint32_t t1_2 = addmw<ON>(t1, t1, o), t0_2 = addmw<ON>(t0, t0, o);
+  uint32_t t4 = addmw<ON>(addmw<ON>(t1_2, t1_2, o), t3, o), t5 = addmw<ON>(addmw<ON>(t0_2, t0_2, o), t2, o);
+  x0 = addmw<ON>(t3, t5, o); x1 = t5; x2 = addmw<ON>(t2, t4, o); x3 = t4;
+}
+template <int ON> __device__ __forceinline__ void mextw(uint32_t* s, uint32_t o) {
+#pragma unroll
+  for (int c = 0; c < 6; ++c) m4w<ON>(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3], o);
+  uint32_t sums[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t a = addmw<ON>(s[k], s[4 + k], o), b = addmw<ON>(s[8 + k], s[12 + k], o), c = addmw<ON>(s[16 + k], s[20 + k], o);
+    sums[k] = addmw<ON>(addmw<ON>(a, b, o), c, o);
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = addmw<ON>(s[i], sums[i & 3], o);
+}
+template <int W> __device__ __forceinline__ void permute_w(uint32_t* s, uint32_t o) {
+  constexpr int W1 = W & 1, W2 = (W >> 1) & 1, W4 = (W >> 2) & 1, W8 = (W >> 3) & 1;
+  const auto& T = ZKB_P2_TABLES;
+  mextw<W4>(s, o);
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sboxw<W1>(addmw<W2>(s[i], T.ext[r * 24 + i], o), o);
+    mextw<W4>(s, o);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 21; ++r) {
+    s[0] = sboxw<W1>(addmw<W2>(reduce_2p(s[0]), T.in[r], o), o);
+    uint32_t tot = addmw<W8>(p2::sum12(s), p2::sum12(s + 12), o);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = addw<W8>(tot, reduce_2p(p2::shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])), o);
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
+#pragma unroll 1
+  for (int r = 4; r < 8; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sboxw<W1>(addmw<W2>(s[i], T.ext[r * 24 + i], o), o);
+    mextw<W4>(s, o);
+  }
+}
+
 constexpr int REPS = 14;       // permutations per thread (a 224-column row)
 template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32_t* out, uint32_t seed, uint32_t z) {
   uint32_t s[24];
@@ -75,7 +159,7 @@ template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32
   for (int rep = 0; rep < REPS; ++rep) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
-    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else permute_v<(V < 0 ? 0 : V)>(s, z);
+    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 1000) permute_w<(V >= 1000 ? V - 1000 : 0)>(s, ~z); else permute_v<(V < 0 || V >= 1000 ? 0 : V)>(s, z);
   }
   uint4* o = reinterpret_cast<uint4*>(out + (size_t)gid * 8);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]); o[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -110,7 +194,17 @@ template <int V, int BLOCK> void run(const char* name) {
   printf("%-52s block %4d regs %3d occ %2d  %8.3f ms  %7.3f Gperm/s  %6.3f T modmul/s  %s\n", name, BLOCK, fa.numRegs, occ, ms, perms / ms / 1e6, perms * 1356 / ms / 1e9, ok ? "OK" : "MISMATCH");
   cudaFree(out);
 }
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {      // short list: the candidates for the library
+    run<-1, 128>("library permute");
+    run<1003, 128>("w3  = w1 + w2");
+    run<1011, 128>("w11 = w1 + w2 + w8");
+    run<1009, 128>("w9  = w1 + w8");
+    run<1003, 256>("w3  = w1 + w2");
+    run<1011, 256>("w11 = w1 + w2 + w8");
+    run<1003, 64>("w3  = w1 + w2");
+    return 0;
+  }
   run<-1, 128>("baseline (library permute)");
   run<0, 128>("v0 same formulation, local code");
   run<1, 128>("v1 canonical product = reduce_2p(lazy)");
@@ -122,7 +216,24 @@ int main() {
   run<15, 128>("v15 all");
   run<9, 128>("v9 = v1 + v8");
   run<11, 128>("v11 = v1 + v2 + v8");
-  run<15, 256>("v15 all");
-  run<7, 256>("v7");
+  run<16 + 10, 128>("v26 = v10 + ALU m in 1 of 4 products");
+  run<32 + 10, 128>("v42 = v10 + ALU m in 2 of 4 products");
+  run<48 + 10, 128>("v58 = v10 + ALU m in 3 of 4 products");
+  run<64 + 10, 128>("v74 = v10 + ALU m in 4 of 4 products");
+  run<64 + 0, 128>("v64 = ALU m in 4 of 4 products, plain adds");
+  run<32 + 0, 128>("v32 = ALU m in 2 of 4 products, plain adds");
+  run<10, 128>("v10 = v2 + v8 (library form)");
+  run<1000, 128>("w0  plain");
+  run<1001, 128>("w1  s-box canonical subtract via VIADDMNMX");
+  run<1002, 128>("w2  round-constant adds via VIADDMNMX");
+  run<1004, 128>("w4  external linear layer via VIADDMNMX");
+  run<1008, 128>("w8  partial rounds via VIADDMNMX");
+  run<1003, 128>("w3  = w1 + w2");
+  run<1007, 128>("w7  = w1 + w2 + w4");
+  run<1015, 128>("w15 all");
+  run<1013, 128>("w13 = w1 + w4 + w8");
+  run<1005, 128>("w5  = w1 + w4");
+  run<1015, 256>("w15 all");
+  run<1007, 256>("w7");
   return 0;
 }

@@ -111,11 +111,12 @@ void ntt_forward_levels(zkb_ctx* ctx, uint32_t* io, size_t count, int k, int exp
 }
 
 // ---- dispatch ---------------------------------------------------------------------------------------------
-bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift);                          // k_ntt_tiled.cu
+bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift, const uint32_t* src);     // k_ntt_tiled.cu
 bool ntt_forward_tiled(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, int k_out, int expand_bits);
 
-void ntt_inverse(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift) {
-  if (ntt_inverse_tiled(ctx, io, count, k, shift)) return;
+void ntt_inverse(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift, const uint32_t* src) {
+  if (ntt_inverse_tiled(ctx, io, count, k, shift, src)) return;
+  if (src && src != io && count) ZKB_CUDA(cudaMemcpyAsync(io, src, (count << k) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   ntt_inverse_levels(ctx, io, count, k, shift);
 }
 // out: count x 2^k_out; in: count x 2^(k_out - expand_bits) (may alias out only when expand_bits == 0)
@@ -138,14 +139,14 @@ zkb_err zkb_batch_interpolate_ntt(zkb_ctx* ctx, void* d_io, size_t count, int po
   ZKB_API_BEGIN use(ctx);
   ZKB_REQUIRE(po2 >= 0 && po2 <= MAX_PO2, "po2 out of range [0, 26]");
   ZKB_REQUIRE((d_io && aligned16(d_io)) || !count, "null or misaligned buffer");
-  ntt_inverse(ctx, (uint32_t*)d_io, count, po2, false);
+  ntt_inverse(ctx, (uint32_t*)d_io, count, po2, false, nullptr);
   ZKB_API_END
 }
 zkb_err zkb_batch_interpolate_ntt_zk_shift(zkb_ctx* ctx, void* d_io, size_t count, int po2) {
   ZKB_API_BEGIN use(ctx);
   ZKB_REQUIRE(po2 >= 0 && po2 <= MAX_PO2, "po2 out of range [0, 26]");
   ZKB_REQUIRE((d_io && aligned16(d_io)) || !count, "null or misaligned buffer");
-  ntt_inverse(ctx, (uint32_t*)d_io, count, po2, true);
+  ntt_inverse(ctx, (uint32_t*)d_io, count, po2, true, nullptr);
   ZKB_API_END
 }
 zkb_err zkb_batch_evaluate_ntt(zkb_ctx* ctx, void* d_io, size_t count, int po2, int expand_bits) {

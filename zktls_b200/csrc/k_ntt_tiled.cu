@@ -220,7 +220,7 @@ template <int A, int TL = 0> struct STile {
 // shared by all columns and stays in L2.
 template <int A, bool INV, int TL = 0, bool TAB = false>
 __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint2* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args,
-                                                                 const uint2* __restrict__ ttab) {
+                                                                 const uint2* __restrict__ ttab, const uint32_t* __restrict__ src) {
   constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
   extern __shared__ uint32_t sm[];
   const uint32_t tid = threadIdx.x;
@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   const uint32_t p2 = (tile << T_LOG) + c2;                                 // position inside the row of S
   const int m_log = A + (int)args.s_log;
   uint32_t* const cb = io + (block << m_log);            // CTA-uniform; everything below is a 32-bit offset (< 2^26 elements)
+  const uint32_t* const cin = src ? src + (block << m_log) : cb;      // inverse pass: optional separate input (the caller's trace), saving a copy
   const uint32_t s_log = args.s_log;
   const uint32_t off_r = (t << s_log) + p2;                // element (r * TPB + t, p2): off_r + r * (TPB << s_log)
   const uint32_t off_c = ((16u * t) << s_log) + p2;        // element (16 t + r, p2):   off_c + (r << s_log)
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   if (INV) {
     constexpr int P0 = A - 4;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = cb[off_r + (((uint32_t)r * TPB) << s_log)];
+    for (int r = 0; r < 16; ++r) v[r] = cin[off_r + (((uint32_t)r * TPB) << s_log)];
     radix_round<true, 0, 4>(v, P0, t, twl);
     int p_prev = P0;
 #pragma unroll
@@ -406,34 +407,34 @@ static bool make_plan(int k, Plan& pl) {
 }
 
 template <int A, bool INV, int TL = 0>
-static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab) {
+static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src) {
   using ST = STile<A, TL>;
   SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
   size_t tile_elems = (size_t)(1 << A) * ST::T;
   size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
   auto kern = ttab ? k_ntt_s<A, INV, TL, true> : k_ntt_s<A, INV, TL, false>;
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab);
+  kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab, src);
   launched(ctx);
 }
 static int s_tile_log() { static int v = [] { const char* e = getenv("ZKB_NTT_S_TLOG"); return e ? atoi(e) : 3; }(); return v; }
 template <bool INV>
-static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab) {
+static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src = nullptr) {
   switch (a) {
-    case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab); break;
-    case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab); break;
-    case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab); break;
-    case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab); break;
-    case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab); break;
+    case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
+    case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
+    case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
+    case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
+    case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
     case 9:
-      if (s_tile_log() == 3) launch_s<9, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
-      else if (s_tile_log() == 2) launch_s<9, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
-      else launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
+      if (s_tile_log() == 3) launch_s<9, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      else if (s_tile_log() == 2) launch_s<9, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      else launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
       break;
     case 10:
-      if (s_tile_log() == 3) launch_s<10, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
-      else if (s_tile_log() == 2) launch_s<10, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
-      else launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab);
+      if (s_tile_log() == 3) launch_s<10, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      else if (s_tile_log() == 2) launch_s<10, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      else launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
       break;
     default: throw Error("zkb200: unsupported strided NTT size");
   }
@@ -469,13 +470,17 @@ static size_t batch_columns(size_t count, size_t bytes_per_column) {
 
 static bool force_levels() { const char* e = getenv("ZKB_NTT_FORCE_LEVELS"); return e && e[0] == '1'; }
 
-bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift) {
+// src (optional): the evaluations are read from src and the coefficients written to io (src is left untouched); when the plan
+// has no strided pass the data is copied first.
+bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shift, const uint32_t* src) {
   Plan pl;
   if (force_levels()) return false;
   if (!make_plan(k, pl)) return false;
   if (count == 0) return true;
   size_t n = (size_t)1 << k;
   if ((count * n) % TILE != 0) return false;          // tiny batches of tiny columns: level path
+  if (src == io) src = nullptr;
+  if (src && pl.n_s == 0) { ZKB_CUDA(cudaMemcpyAsync(io, src, count * n * 4, cudaMemcpyDeviceToDevice, ctx->stream)); src = nullptr; }
   NttTables* t = ntt_tables(ctx);
   TwiddleRef tw{t->d_hi, t->d_lo};
   const uint2* twl = level_table(ctx, true);
@@ -504,7 +509,7 @@ bool ntt_inverse_tiled(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool shi
     size_t cols = std::min(bc, count - c0);
     uint32_t* p = io + c0 * n;
     size_t total = cols * n;
-    for (int i = 0; i < pl.n_s; ++i) dispatch_s<true>(ctx, sp[i].a, p, total, sp[i].s_log, twl, tw, sp[i].table, sp[i].shift_g, sp[i].ttab);
+    for (int i = 0; i < pl.n_s; ++i) dispatch_s<true>(ctx, sp[i].a, p, total, sp[i].s_log, twl, tw, sp[i].table, sp[i].shift_g, sp[i].ttab, (i == 0 && src) ? src + c0 * n : nullptr);
     if (epi == EPI_TABLE) dispatch_c_inv<EPI_TABLE>(ctx, pl.a_c, p, total, twl, c_table, 0);
     else if (epi == EPI_SCALE) dispatch_c_inv<EPI_SCALE>(ctx, pl.a_c, p, total, twl, nullptr, scale.v);
     else dispatch_c_inv<EPI_NONE>(ctx, pl.a_c, p, total, twl, nullptr, 0);

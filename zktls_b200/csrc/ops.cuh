@@ -7,7 +7,8 @@
 namespace zkb {
 
 // k_ntt.cu
-void ntt_inverse(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool zk_shift);
+// src (optional, device): read the evaluations from src instead of io (out of place; src is left untouched)
+void ntt_inverse(zkb_ctx* ctx, uint32_t* io, size_t count, int k, bool zk_shift, const uint32_t* src = nullptr);
 void ntt_forward(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, int k_out, int expand_bits);
 // k_poseidon2.cu
 void hash_rows(zkb_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols);

@@ -49,11 +49,27 @@ ZKB_HD uint32_t sum12(const uint32_t* s) {
   return add_mod(reduce_2p(reduce_2p((uint32_t)acc)), reduce_2p((uint32_t)(acc >> 32) * R_MOD_P));
 }
 
-ZKB_HD uint32_t sbox7(uint32_t x) {
-  uint32_t x2 = mont_mul(x, x);
+// Pipe assignment (sm_100a).  ncu on k_hash_rows: the fmaheavy pipe (every IMAD form) is ~90 % busy and the ALU pipe is the
+// other half of a balanced pair (VIADDMNMX takes two ALU issue slots), yet ptxas turns ~45 % of the plain two-input
+// additions into IMAD.IADD.  `min(a + b, ones)` with ones = 0xffffffff held in a uniform register (a launch argument, so it
+// cannot be folded) compiles to ONE VIADDMNMX.U32 Rd, Ra, +-Rb, URones: a two-input add that stays on the ALU pipe.  Used for
+// the s-box's canonical products, the round-constant additions and the partial rounds (+6.5 % permutations/s); the
+// external linear layer is left to ptxas -- forcing its 128 additions per round onto the ALU pipe overloads it (-9 %).
+// Measurements: tools/ubench/p2_alu_adds.cu, profiles/r1_r_ubench_p2_alu_adds.txt.  On the host `ones` is a constant.
+ZKB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+ZKB_HD uint32_t add_alu(uint32_t a, uint32_t b, uint32_t ones) { return umin32(a + b, ones); }
+ZKB_HD uint32_t mont_mul_alu(uint32_t a, uint32_t b, uint32_t ones) {      // mont_mul with the final subtraction on the ALU pipe
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = (uint32_t)t * P_INV;
+  uint32_t r = umin32((uint32_t)(t >> 32) - mul_hi32(m, P), ones);
+  uint32_t y = r + P;
+  return y < r ? y : r;
+}
+ZKB_HD uint32_t sbox7(uint32_t x, uint32_t ones = 0xffffffffu) {
+  uint32_t x2 = mont_mul_alu(x, x, ones);
   uint32_t x4 = mont_mul_lazy(x2, x2);     // < 2P
   uint32_t x6 = mont_mul_lazy(x4, x2);     // x4 < 2P, x2 < P
-  return mont_mul(x6, x);                  // x6 < 2P, x < P
+  return mont_mul_alu(x6, x, ones);        // x6 < 2P, x < P
 }
 
 // 4x4 MDS block [5 7 1 3; 4 6 1 1; 1 3 5 7; 1 1 4 6]
@@ -77,17 +93,13 @@ ZKB_HD void m_ext(uint32_t* s) {
   for (int i = 0; i < 24; ++i) s[i] = add_mod(s[i], sums[i & 3]);
 }
 
-// `z` is a zero the compiler cannot see through (the kernels pass a launch argument).  ptxas turns about a quarter of the
-// plain two-input additions into IMAD.IADD, i.e. onto the multiplier pipe the s-boxes saturate; writing the additions next
-// to the s-boxes and in the partial rounds as a + b + z keeps them 3-input IADD3s on the ALU pipe (+1.2 % permutations/s;
-// doing the same inside the external linear layer overloads the ALU pipe instead: -4 %, tools/ubench/p2_alu_adds.cu).
 template <typename Tables>
-ZKB_HD void permute(uint32_t* s, const Tables& T, const uint32_t z = 0u) {
+ZKB_HD void permute(uint32_t* s, const Tables& T, const uint32_t ones = 0xffffffffu) {
   m_ext(s);
 #pragma unroll 1
   for (int r = 0; r < 4; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(s[i] + T.ext[r * 24 + i] + z));
+    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(add_alu(s[i], T.ext[r * 24 + i], ones)), ones);
     m_ext(s);
   }
   // Partial rounds.  Cells are kept LAZY (in [0, 2P)) across these rounds: only cell 0 is made canonical for its
@@ -95,17 +107,17 @@ ZKB_HD void permute(uint32_t* s, const Tables& T, const uint32_t z = 0u) {
   // once to [0, P) -- so tot + product < 2P again with no second correction.
 #pragma unroll 1
   for (int r = 0; r < 21; ++r) {
-    s[0] = sbox7(reduce_2p(reduce_2p(s[0]) + T.in[r] + z));
-    uint32_t tot = reduce_2p(sum12(s) + sum12(s + 12) + z);
+    s[0] = sbox7(reduce_2p(add_alu(reduce_2p(s[0]), T.in[r], ones)), ones);
+    uint32_t tot = reduce_2p(add_alu(sum12(s), sum12(s + 12), ones));
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = tot + reduce_2p(shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])) + z;
+    for (int i = 0; i < 24; ++i) s[i] = add_alu(tot, reduce_2p(shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])), ones);
   }
 #pragma unroll
   for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
 #pragma unroll 1
   for (int r = 4; r < 8; ++r) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(s[i] + T.ext[r * 24 + i] + z));
+    for (int i = 0; i < 24; ++i) s[i] = sbox7(reduce_2p(add_alu(s[i], T.ext[r * 24 + i], ones)), ones);
     m_ext(s);
   }
 }

@@ -209,9 +209,10 @@ struct zkb_prover {
     PhaseTimer pt(ctx);
     size_t cols = circuit.group_size[g];
     DevBuf c(ctx, cols * n);
-    if (cols) ZKB_CUDA(cudaMemcpyAsync(c.p, trace, cols * n * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    // a trace that is already on the device is read in place by the first iNTT pass (no device-to-device copy)
+    if (cols && !on_device) ZKB_CUDA(cudaMemcpyAsync(c.p, trace, cols * n * 4, cudaMemcpyHostToDevice, ctx->stream));
     pt.mark("commit_group: upload");
-    ntt_inverse(ctx, c.p, cols, po2, true);
+    ntt_inverse(ctx, c.p, cols, po2, true, on_device ? (const uint32_t*)trace : nullptr);
     pt.mark("commit_group: iNTT+zk_shift");
     groups[g].build(ctx, std::move(c), cols, po2);
     pt.mark("commit_group: LDE+hash+merkle");
