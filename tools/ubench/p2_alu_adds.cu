@@ -110,20 +110,28 @@ template <int ON> __device__ __forceinline__ void m4w(uint32_t& x0, uint32_t& x1
   uint32_t t4 = addmw<ON>(addmw<ON>(t1_2, t1_2, o), t3, o), t5 = addmw<ON>(addmw<ON>(t0_2, t0_2, o), t2, o);
   x0 = addmw<ON>(t3, t5, o); x1 = t5; x2 = addmw<ON>(t2, t4, o); x3 = t4;
 }
+// ON bits: 1 = the six 4x4 blocks, 2 = the column sums, 4 = the final 24 additions; 8 = only the first half of every 4x4 block
+template <int ON> __device__ __forceinline__ void m4h(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t o) {
+  uint32_t t0 = addmw<1>(x0, x1, o), t1 = addmw<1>(x2, x3, o);
+  uint32_t t2 = addmw<1>(addmw<1>(x1, x1, o), t1, o), t3 = addmw<1>(addmw<1>(x3, x3, o), t0, o);
+  uint32_t t1_2 = addmw<0>(t1, t1, o), t0_2 = addmw<0>(t0, t0, o);
+  uint32_t t4 = addmw<0>(addmw<0>(t1_2, t1_2, o), t3, o), t5 = addmw<0>(addmw<0>(t0_2, t0_2, o), t2, o);
+  x0 = addmw<0>(t3, t5, o); x1 = t5; x2 = addmw<0>(t2, t4, o); x3 = t4;
+}
 template <int ON> __device__ __forceinline__ void mextw(uint32_t* s, uint32_t o) {
 #pragma unroll
-  for (int c = 0; c < 6; ++c) m4w<ON>(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3], o);
+  for (int c = 0; c < 6; ++c) { if (ON & 8) m4h<1>(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3], o); else m4w<(ON & 1)>(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3], o); }
   uint32_t sums[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    uint32_t a = addmw<ON>(s[k], s[4 + k], o), b = addmw<ON>(s[8 + k], s[12 + k], o), c = addmw<ON>(s[16 + k], s[20 + k], o);
-    sums[k] = addmw<ON>(addmw<ON>(a, b, o), c, o);
+    uint32_t a = addmw<((ON >> 1) & 1)>(s[k], s[4 + k], o), b = addmw<((ON >> 1) & 1)>(s[8 + k], s[12 + k], o), c = addmw<((ON >> 1) & 1)>(s[16 + k], s[20 + k], o);
+    sums[k] = addmw<((ON >> 1) & 1)>(addmw<((ON >> 1) & 1)>(a, b, o), c, o);
   }
 #pragma unroll
-  for (int i = 0; i < 24; ++i) s[i] = addmw<ON>(s[i], sums[i & 3], o);
+  for (int i = 0; i < 24; ++i) s[i] = addmw<((ON >> 2) & 1)>(s[i], sums[i & 3], o);
 }
 template <int W> __device__ __forceinline__ void permute_w(uint32_t* s, uint32_t o) {
-  constexpr int W1 = W & 1, W2 = (W >> 1) & 1, W4 = (W >> 2) & 1, W8 = (W >> 3) & 1;
+  constexpr int W1 = W & 1, W2 = (W >> 1) & 1, W4 = ((W >> 2) & 1) ? 7 : (W >> 4), W8 = (W >> 3) & 1;      // W >> 4: linear-layer sub-selection (mextw ON bits)
   const auto& T = ZKB_P2_TABLES;
   mextw<W4>(s, o);
 #pragma unroll 1
@@ -202,7 +210,12 @@ int main(int argc, char** argv) {
     run<1009, 128>("w9  = w1 + w8");
     run<1003, 256>("w3  = w1 + w2");
     run<1011, 256>("w11 = w1 + w2 + w8");
-    run<1003, 64>("w3  = w1 + w2");
+    run<1011 + 16 * 1, 256>("w11 + the 4x4 blocks");
+    run<1011 + 16 * 2, 256>("w11 + column sums");
+    run<1011 + 16 * 4, 256>("w11 + final 24 additions");
+    run<1011 + 16 * 6, 256>("w11 + column sums + final additions");
+    run<1011 + 16 * 8, 256>("w11 + first half of the 4x4 blocks");
+    run<1011 + 16 * 12, 256>("w11 + first half of the 4x4 blocks + final additions");
     return 0;
   }
   run<-1, 128>("baseline (library permute)");

@@ -91,10 +91,21 @@ const char* PREAMBLE = R"(
 typedef unsigned int u32; typedef unsigned long long u64;
 #define P 2013265921u
 #define NB 1073741848u   /* Montgomery form of -11 (Fp4 = Fp[x]/(x^4+11)) */
+// Two-input additions / subtractions are written min(a +- b, ONES) with ONES = 0xffffffff read from the constant bank (opaque
+// to the compiler): ptxas emits ONE VIADDMNMX (ALU pipe) for it and cannot choose IMAD.IADD, which would land on the
+// multiplier pipe this kernel is bound by (see poseidon2.cuh).  ZKB_EC_ALU_ADDS=0 restores plain additions.
+__constant__ u32 zkb_ones = 0xffffffffu;
+#if ZKB_ALU_ADDS
+#define ADD2(a, b) min((a) + (b), zkb_ones)
+#define SUB2(a, b) min((a) - (b), zkb_ones)
+#else
+#define ADD2(a, b) ((a) + (b))
+#define SUB2(a, b) ((a) - (b))
+#endif
 __device__ __forceinline__ u32 red(u32 x) { return min(x, x - P); }
-__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; u32 r = (u32)(t >> 32) - __umulhi(m, P); return min(r, r + P); }
-__device__ __forceinline__ u32 add(u32 a, u32 b) { return red(a + b); }
-__device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = a - b; return min(d, d + P); }
+__device__ __forceinline__ u32 mul(u32 a, u32 b) { u64 t = (u64)a * b; u32 m = (u32)t * 0x88000001u; u32 r = SUB2((u32)(t >> 32), __umulhi(m, P)); return min(r, r + P); }
+__device__ __forceinline__ u32 add(u32 a, u32 b) { return red(ADD2(a, b)); }
+__device__ __forceinline__ u32 sub(u32 a, u32 b) { u32 d = SUB2(a, b); return min(d, d + P); }
 // Lazy accumulation of sum_k pw_k * f_k (pw_k, f_k canonical): a 64-bit accumulator per Fp4 component takes one
 // IMAD.WIDE per term; after every second term its high word is brought back below P (one VIADDMNMX), which keeps the
 // accumulator below P * 2^32 + 2 P^2 < 2^64; a single Montgomery reduction at the end of the chain gives the canonical
@@ -103,7 +114,7 @@ __device__ __forceinline__ u64 wide(u32 f, u32 w) { return (u64)f * w; }
 __device__ __forceinline__ u64 widem(u32 m, u32 f, u32 w) { return ((u64)m << 32) + (u64)f * w; }
 __device__ __forceinline__ void wacc(u64& a, u32 f, u32 w) { a += (u64)f * w; }
 __device__ __forceinline__ u64 fixhi(u64 a) { u32 hi = (u32)(a >> 32); hi = min(hi, hi - P); return ((u64)hi << 32) | (u32)a; }
-__device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x88000001u; u32 r = (u32)(a >> 32) - __umulhi(m, P); return min(r, r + P); }
+__device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x88000001u; u32 r = SUB2((u32)(a >> 32), __umulhi(m, P)); return min(r, r + P); }
 __device__ __forceinline__ void st(u32* p, u32 v) { *p = v; }
 )";
 
@@ -301,9 +312,9 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
       halo = std::max(halo, 4 * t.back);
     }
     const uint32_t res_max = env_u32("ZKB_EC_RES", 32, 0, 64), res_min_uses = env_u32("ZKB_EC_RES_USES", 4, 2, 1u << 30);
-    // measured on B200, SYN-280 (profiles/r1_o_ec_staged.txt): 3 stages x 6 columns = 1.89 ms (34 KB per CTA, six CTAs per SM); deeper or
-    // wider rings cost occupancy (6 x 8: 3.25 ms, 10 x 8: 4.35 ms), the register form above takes 2.51 ms
-    cps = env_u32("ZKB_EC_CPS", 6, 1, 32); stages = env_u32("ZKB_EC_STAGES", 3, 2, 16);
+    // measured on B200, SYN-280 (profiles/r1_o_ec_staged.txt): 2 stages x 6 columns = 1.82 ms (28 KB per CTA: eight CTAs = 2048 threads per
+    // SM), 3 x 6: 1.89-1.96 ms; deeper or wider rings cost occupancy (6 x 8: 3.25 ms, 10 x 8: 4.35 ms); the register form takes 2.4-2.5 ms
+    cps = env_u32("ZKB_EC_CPS", 6, 1, 32); stages = env_u32("ZKB_EC_STAGES", 2, 2, 16);
     std::vector<ColUse> cand;
     for (auto& kv : uses) if (kv.second >= res_min_uses) cand.push_back({kv.first.first, kv.first.second, kv.second});
     std::stable_sort(cand.begin(), cand.end(), [](const ColUse& x, const ColUse& y) { return x.uses > y.uses; });
@@ -330,7 +341,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
     gi.block = SG_BLOCK; gi.staged = true;
   }
   std::ostringstream o;
-  o << PREAMBLE;
+  o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
   if (staged) o << "#define HALO " << halo << "u\n#define BLOCK " << SG_BLOCK << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
   if (vec) o << preamble_rows(rows) << "typedef FV RV; typedef AV ACC;\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) ldv(p)\n";
   else o << "typedef u32 RV; typedef u64 ACC;\n#define W0(f, w) wide(f, w)\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) __ldg(p)\n";
