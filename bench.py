@@ -168,7 +168,7 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
@@ -196,9 +196,22 @@ def main():
     dev = torch.device("cuda", local_rank)
     pin_rank_to_gpu_numa_node(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # the version banner goes to stdout; stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION from the environment or from
+        # /etc/nccl.conf) is printed to stdout when the first communicator is created, so (i) ask for WARN unless the user
+        # wants more, and (ii) point fd 1 at stderr while the communicator comes up
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
@@ -342,19 +355,22 @@ def main():
         alg_bytes = 4 * rows * cols + 32 * rows
         achieved = alg_bytes / (ms * 1e-3) / 1e9
         perms = rows * ((cols + 15) // 16)
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_h_hash_rows_traffic.json")     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-        if po2 == PO2 and os.path.exists(tpath):
+        traffic, traffic_src, ncu_pipes = None, None, None
+        import glob
+        tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_hash_rows_traffic.json")))     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture per round
+        tpath = tpaths[-1] if tpaths else ""
+        if po2 == PO2 and tpath:
             with open(tpath) as f:
                 tj = json.load(f)
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+            ncu_pipes = {k: tj[k] for k in ("sm__pipe_fmaheavy_cycles_active_pct", "sm__pipe_alu_cycles_active_pct", "smsp__issue_active_pct") if k in tj}
         roof = {"bound": "hbm", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                 "peak_source": peak_kind, "ms_per_launch": ms,
                 "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation; peak = measured "
                                   "pure Montgomery-modmul stream on B200 (profiles/r1_ubench_fp64_mix.txt)",
                           "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3), "peak_modmul_per_s": INT32_MODMUL_PEAK,
-                          "frac": 1356 * perms / (ms * 1e-3) / INT32_MODMUL_PEAK}}
+                          "frac": 1356 * perms / (ms * 1e-3) / INT32_MODMUL_PEAK, "ncu_pipe_utilisation": ncu_pipes}}
         del mat, dig
         # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT and x4 LDE over 64 columns of 2^20
         ntt_cols = 224

@@ -130,6 +130,13 @@ zkb_err zkb_eval_check(zkb_ctx* ctx, void* d_check, const uint32_t* h_circuit, s
  * crate build time. */
 zkb_err zkb_eval_check_source(const uint32_t* h_circuit, size_t circuit_words, char* out, size_t cap, size_t* needed);
 zkb_err zkb_eval_check_precompile(const uint32_t* h_circuit, size_t circuit_words);
+/* CircuitHal::accumulate(ctrl, io, data, mix, accum, steps) (risc0-circuit-rv32im `prove/hal/{cpu,cuda}.rs`, run by
+ * prove_segment between the data commit and the accum commit; in-tree call site crates/guest-prover-r0/src/prover.rs:90):
+ * fills the accum group's columns on the device from the code (= ctrl) and data traces, the `mix` globals that
+ * zkb_prover_segment_begin returned, and io.  Rows the circuit leaves unconstrained keep the caller's contents.  The
+ * witness program belongs to the circuit: built in for the SYN family, an error string for any other circuit info. */
+zkb_err zkb_accumulate(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_words, void* d_accum, const void* d_code,
+                       const void* d_data, const uint32_t* h_mix, const uint32_t* h_io, int po2);
 
 /* ---- Prover: risc0-zkp prove::Prover + the circuit's prove_segment driver ------------------ */
 zkb_err zkb_prover_new(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_words, zkb_prover** out);

@@ -118,3 +118,32 @@ impl Hal for B200Hal {
         ok(unsafe { sys::zkb_scatter(self.ctx, into.as_device_ptr(), into.size(), index.as_ptr(), index.len() - 1, offsets.as_ptr(), values.as_ptr() as *const u32) })
     }
 }
+
+/// B200CircuitHal: risc0_zkp::hal::CircuitHal<B200Hal> for a circuit described by a blob (TapSet + PolyExtStep program).
+/// SOURCE ONLY, like the rest of this file.  `blob` is built once per circuit from `CircuitDef::{taps, poly_ext}`.
+pub struct B200CircuitHal { ctx: *mut sys::ZkbCtx, blob: Vec<u32> }
+
+impl B200CircuitHal {
+    pub fn new(hal: &B200Hal, blob: Vec<u32>) -> Self {
+        ok(unsafe { sys::zkb_eval_check_precompile(blob.as_ptr(), blob.len()) });     // NVRTC-specialise eval_check ahead of the first proof
+        Self { ctx: hal.ctx, blob }
+    }
+}
+
+impl risc0_zkp::hal::CircuitHal<B200Hal> for B200CircuitHal {
+    /// groups = [accum, code, data] LDE matrices; globals = [mix, out] host-visible (small) buffers
+    fn eval_check(&self, check: &B200Buffer<BabyBearElem>, groups: &[&B200Buffer<BabyBearElem>], globals: &[&B200Buffer<BabyBearElem>],
+                  poly_mix: BabyBearExtElem, po2: usize, _steps: usize) {
+        let (mix, out) = (globals[0].to_vec(), globals[1].to_vec());
+        ok(unsafe { sys::zkb_eval_check(self.ctx, check.as_device_ptr(), self.blob.as_ptr(), self.blob.len(), groups[0].as_device_ptr(), groups[1].as_device_ptr(),
+                                        groups[2].as_device_ptr(), mix.as_ptr() as *const u32, out.as_ptr() as *const u32, &poly_mix as *const _ as *const u32, po2 as i32) })
+    }
+    /// ctrl = the code trace.  The witness program is the circuit's: libzkb200 carries the SYN family's; the rv32im step functions
+    /// (`step_compute_accum` / `step_verify_accum`) would be added to csrc/k_accum.cu the same way eval_check takes `poly_ext` as data.
+    fn accumulate(&self, ctrl: &B200Buffer<BabyBearElem>, io: &B200Buffer<BabyBearElem>, data: &B200Buffer<BabyBearElem>, mix: &B200Buffer<BabyBearElem>,
+                  accum: &B200Buffer<BabyBearElem>, steps: usize) {
+        let (mix, io) = (mix.to_vec(), io.to_vec());
+        ok(unsafe { sys::zkb_accumulate(self.ctx, self.blob.as_ptr(), self.blob.len(), accum.as_device_ptr(), ctrl.as_device_ptr(), data.as_device_ptr(),
+                                        mix.as_ptr() as *const u32, io.as_ptr() as *const u32, log2_ceil(steps) as i32) })
+    }
+}

@@ -52,6 +52,7 @@ extern "C" {
     pub fn zkb_eval_check(ctx: *mut ZkbCtx, d_check: *mut c_void, h_circuit: *const u32, circuit_words: usize, d_accum: *const c_void, d_code: *const c_void, d_data: *const c_void, h_mix_g: *const u32, h_out_g: *const u32, h_poly_mix: *const u32, po2: c_int) -> ZkbErr;
     pub fn zkb_eval_check_source(h_circuit: *const u32, circuit_words: usize, out: *mut c_char, cap: usize, needed: *mut usize) -> ZkbErr;
     pub fn zkb_eval_check_precompile(h_circuit: *const u32, circuit_words: usize) -> ZkbErr;
+    pub fn zkb_accumulate(ctx: *mut ZkbCtx, h_circuit: *const u32, circuit_words: usize, d_accum: *mut c_void, d_code: *const c_void, d_data: *const c_void, h_mix: *const u32, h_io: *const u32, po2: c_int) -> ZkbErr;
     pub fn zkb_prover_new(ctx: *mut ZkbCtx, h_circuit: *const u32, circuit_words: usize, out: *mut *mut ZkbProver) -> ZkbErr;
     pub fn zkb_prover_free(p: *mut ZkbProver) -> ZkbErr;
     pub fn zkb_prover_segment_begin(p: *mut ZkbProver, po2: c_int, h_io: *const u32, code: *const c_void, data: *const c_void, traces_on_device: c_int, h_mix_out: *mut u32) -> ZkbErr;

@@ -1,0 +1,70 @@
+"""CircuitHal::accumulate on the device (zkb_accumulate, csrc/k_accum.cu) against the host witness generator
+(zktls_b200/synth.py trace_b_accum, the numpy statement of the SYN family's accumulation step), and as the middle step of a
+segment proof that never brings the accum trace to the host."""
+import numpy as np
+import pytest
+
+from zktls_b200 import circuit, synth
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(accum_cols=4, code_cols=3, data_cols=6, mix_size=5, out_size=4)
+MID = dict(accum_cols=7, code_cols=5, data_cols=33, mix_size=20, out_size=32)
+ONE = dict(accum_cols=1, code_cols=2, data_cols=1, mix_size=1, out_size=1)
+
+
+@pytest.fixture(scope="module")
+def hal():
+    from zktls_b200.hal import B200Hal
+    h = B200Hal(0)
+    yield h
+    h.close()
+
+
+@pytest.mark.parametrize("shape,po2", [(ONE, 7), (SMALL, 6), (SMALL, 11), (MID, 12), (circuit.SYN280, 10)])
+def test_accumulate_matches_host_witness_generator(hal, shape, po2):
+    blob = circuit.syn_circuit(**shape).blob()
+    io, code, data = synth.trace_b_code_data(shape, po2, seed=3 + po2)
+    mix = synth.encode(synth.splitmix_fp(99 + po2, shape["mix_size"])).astype(np.uint32)      # any Montgomery words: the op does not care where mix came from
+    want = synth.to_mont(synth.trace_b_accum(shape, po2, 3 + po2, code, data, io, mix))
+    # the device op overwrites live rows only: start from the same noise the host generator starts from
+    n = 1 << po2
+    noise = synth.to_mont(synth.splitmix_fp((3 + po2) * 4 + 3, shape["accum_cols"] * n).reshape(shape["accum_cols"], n))
+    accum = hal.copy_from_elem(noise)
+    hal.accumulate(blob, accum, hal.copy_from_elem(synth.to_mont(code)), hal.copy_from_elem(synth.to_mont(data)), mix, io, po2)
+    got = accum.to_numpy()
+    assert np.array_equal(got, want)
+    live = code[0].astype(bool)
+    assert np.array_equal(got.reshape(-1, n)[:, ~live], noise.reshape(-1, n)[:, ~live]), "rows outside the selector must be left alone"
+
+
+def test_accumulate_is_rejected_for_a_circuit_without_a_witness_program(hal):
+    from zktls_b200._lib import ZkbError
+    b = circuit.syn_circuit(**SMALL)
+    b.info = b"RV32IM:v1_______"
+    blob = b.blob()
+    buf = hal.alloc_elem(4 << 6)
+    with pytest.raises(ZkbError, match="no witness program"):
+        hal.accumulate(blob, buf, buf, buf, np.zeros(5, np.uint32), np.zeros(4, np.uint32), 6)
+
+
+@pytest.mark.parametrize("shape,po2", [(SMALL, 9), (MID, 12)])
+def test_segment_proof_with_device_side_accumulate(hal, oracle, shape, po2):
+    """begin() -> accumulate on the device -> finish(device buffer): the seal equals the oracle's (host accum) and verifies."""
+    from zktls_b200.prover import SegmentProver, verify_segment
+    blob = circuit.syn_circuit(**shape).blob()
+    io, code, data = synth.trace_b_code_data(shape, po2, seed=21)
+    code_m, data_m = synth.to_mont(code), synth.to_mont(data)
+    d_code, d_data = hal.copy_from_elem(code_m), hal.copy_from_elem(data_m)
+    gp = SegmentProver(hal, blob)
+    mix = gp.begin(po2, io, d_code, d_data)
+    n = 1 << po2
+    d_accum = hal.copy_from_elem(synth.to_mont(synth.splitmix_fp(21 * 4 + 3, shape["accum_cols"] * n).reshape(shape["accum_cols"], n)))
+    hal.accumulate(blob, d_accum, d_code, d_data, mix, io, po2)
+    seal = gp.finish(d_accum)
+    op = oracle.Prover(blob)
+    assert np.array_equal(op.begin(po2, io, code_m, data_m), mix)
+    seal_o = op.finish(synth.to_mont(synth.trace_b_accum(shape, po2, 21, code, data, io, mix)))
+    assert np.array_equal(seal, seal_o)
+    verify_segment(blob, seal)
+    gp.close()

@@ -205,6 +205,13 @@ class B200Hal:
         check(lib().zkb_scatter(self.ctx, C.c_void_p(into.ptr), _sz(into.size), _hp(ix), _sz(max(ix.size - 1, 0)), _hp(of), _hp(va)))
 
     # ---- CircuitHal ---------------------------------------------------------------------------------------------
+    def accumulate(self, circuit_blob, accum, code, data, mix_g, out_g, po2):
+        """CircuitHal::accumulate: fills `accum` (device, column-major) from the code / data traces and the mix / io globals."""
+        blob = np.ascontiguousarray(circuit_blob, np.uint32)
+        mg = np.ascontiguousarray(mix_g, np.uint32); og = np.ascontiguousarray(out_g, np.uint32)
+        check(lib().zkb_accumulate(self.ctx, _hp(blob), _sz(blob.size), C.c_void_p(accum.ptr), C.c_void_p(code.ptr), C.c_void_p(data.ptr),
+                                   _hp(mg), _hp(og), C.c_int(po2)))
+
     def eval_check(self, check_buf, circuit_blob, accum, code, data, mix_g, out_g, poly_mix, po2):
         blob = np.ascontiguousarray(circuit_blob, np.uint32)
         mg = np.ascontiguousarray(mix_g, np.uint32); og = np.ascontiguousarray(out_g, np.uint32); pm = np.ascontiguousarray(poly_mix, np.uint32)
