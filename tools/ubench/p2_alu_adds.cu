@@ -157,6 +157,55 @@ template <int W> __device__ __forceinline__ void permute_w(uint32_t* s, uint32_t
   }
 }
 
+// ---- third family: w11 plus the Montgomery factor m = lo * P^-1 = lo + (lo << 27) + (lo << 31) built from two shifts and two
+// VIADDMNMX additions (4 ALU instructions instead of 1 IMAD) in the first NM products of every s-box.
+template <int ON> __device__ __forceinline__ uint32_t m_sel(uint32_t lo, uint32_t ones) {
+  if (!ON) return lo * P_INV;
+  uint32_t s1 = min(lo + (lo << 27), ones);
+  return min(s1 + (lo << 31), ones);
+}
+template <int ON> __device__ __forceinline__ uint32_t mmx_canon(uint32_t a, uint32_t b, uint32_t ones) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = m_sel<ON>((uint32_t)t, ones);
+  uint32_t r = min((uint32_t)(t >> 32) - mul_hi32(m, P), ones);
+  uint32_t y = r + P;
+  return y < r ? y : r;
+}
+template <int ON> __device__ __forceinline__ uint32_t mmx_lazy(uint32_t a, uint32_t b, uint32_t ones) {
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = m_sel<ON>((uint32_t)t, ones);
+  return (uint32_t)(t >> 32) - mul_hi32(m, P) + P;
+}
+template <int NM> __device__ __forceinline__ uint32_t sboxx(uint32_t x, uint32_t ones) {
+  uint32_t x2 = mmx_canon<(NM >= 1)>(x, x, ones), x4 = mmx_lazy<(NM >= 2)>(x2, x2, ones), x6 = mmx_lazy<(NM >= 3)>(x4, x2, ones);
+  return mmx_canon<(NM >= 4)>(x6, x, ones);
+}
+template <int NM> __device__ __forceinline__ void permute_x(uint32_t* s, uint32_t o) {
+  const auto& T = ZKB_P2_TABLES;
+  p2::m_ext(s);
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sboxx<NM>(addmw<1>(s[i], T.ext[r * 24 + i], o), o);
+    p2::m_ext(s);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 21; ++r) {
+    s[0] = sboxx<NM>(addmw<1>(reduce_2p(s[0]), T.in[r], o), o);
+    uint32_t tot = addmw<1>(p2::sum12(s), p2::sum12(s + 12), o);
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = addw<1>(tot, reduce_2p(p2::shoup_mul_lazy(s[i], T.diag[i], T.diag_q[i])), o);
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s[i] = reduce_2p(s[i]);
+#pragma unroll 1
+  for (int r = 4; r < 8; ++r) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = sboxx<NM>(addmw<1>(s[i], T.ext[r * 24 + i], o), o);
+    p2::m_ext(s);
+  }
+}
+
 constexpr int REPS = 14;       // permutations per thread (a 224-column row)
 template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32_t* out, uint32_t seed, uint32_t z) {
   uint32_t s[24];
@@ -167,7 +216,7 @@ template <int V, int BLOCK> __global__ void __launch_bounds__(BLOCK) kern(uint32
   for (int rep = 0; rep < REPS; ++rep) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) s[i] = (gid * 2654435761u + (uint32_t)(rep * 16 + i) * 40503u + seed) % P;
-    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 1000) permute_w<(V >= 1000 ? V - 1000 : 0)>(s, ~z); else permute_v<(V < 0 || V >= 1000 ? 0 : V)>(s, z);
+    if (V < 0) p2::permute(s, ZKB_P2_TABLES); else if (V >= 2000) permute_x<(V >= 2000 ? V - 2000 : 0)>(s, ~z); else if (V >= 1000 && V < 2000) permute_w<(V >= 1000 && V < 2000 ? V - 1000 : 0)>(s, ~z); else permute_v<(V < 0 || V >= 1000 ? 0 : V)>(s, z);
   }
   uint4* o = reinterpret_cast<uint4*>(out + (size_t)gid * 8);
   o[0] = make_uint4(s[0], s[1], s[2], s[3]); o[1] = make_uint4(s[4], s[5], s[6], s[7]);
@@ -210,6 +259,12 @@ int main(int argc, char** argv) {
     run<1009, 128>("w9  = w1 + w8");
     run<1003, 256>("w3  = w1 + w2");
     run<1011, 256>("w11 = w1 + w2 + w8");
+    run<2000, 256>("x0 = w11 (local code)");
+    run<2001, 256>("x1 = w11 + shift-add m in 1 of 4 products");
+    run<2002, 256>("x2 = w11 + shift-add m in 2 of 4 products");
+    run<2003, 256>("x3 = w11 + shift-add m in 3 of 4 products");
+    run<2004, 256>("x4 = w11 + shift-add m in 4 of 4 products");
+    if (argc > 2) return 0;
     run<1011 + 16 * 1, 256>("w11 + the 4x4 blocks");
     run<1011 + 16 * 2, 256>("w11 + column sums");
     run<1011 + 16 * 4, 256>("w11 + final 24 additions");

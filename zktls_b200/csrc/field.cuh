@@ -56,6 +56,18 @@ ZKB_HD uint32_t mont_mul(uint32_t a, uint32_t b) {
 // product left in (0, 2P); same precondition
 ZKB_HD uint32_t mont_mul_lazy(uint32_t a, uint32_t b) { return mont_redc_lazy((uint64_t)a * b); }
 ZKB_HD uint32_t add_mod(uint32_t a, uint32_t b) { return reduce_2p(a + b); }
+// ALU-pinned forms (see the pipe-assignment note in poseidon2.cuh): `ones` must be 0xffffffff and must reach the kernel as a
+// launch argument, so that min(a + b, ones) survives as ONE VIADDMNMX instead of being folded into an add ptxas may turn into IMAD.IADD.
+ZKB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+ZKB_HD uint32_t add_alu(uint32_t a, uint32_t b, uint32_t ones) { return umin32(a + b, ones); }
+ZKB_HD uint32_t mont_mul_alu(uint32_t a, uint32_t b, uint32_t ones) {      // mont_mul with the final subtraction on the ALU pipe
+  uint64_t t = (uint64_t)a * b;
+  uint32_t m = (uint32_t)t * P_INV;
+  uint32_t r = umin32((uint32_t)(t >> 32) - mul_hi32(m, P), ones);
+  uint32_t y = r + P;
+  return y < r ? y : r;
+}
+
 ZKB_HD uint32_t sub_mod(uint32_t a, uint32_t b) {
   uint32_t d = a - b;
   uint32_t e = d + P;

@@ -28,6 +28,8 @@ namespace zkb {
 constexpr int TILE_LOG = 12, TILE = 1 << TILE_LOG;      // elements per CTA in pass C
 constexpr int C_THREADS = TILE / 16;                    // 256
 constexpr int MAX_LEVEL_LOG = 12;                       // level tables cover q < 12
+// the all-ones launch argument of the ALU-pinned additions in radix_round
+static inline uint32_t ntt_ones() { return 0xffffffffu; }
 
 __device__ __forceinline__ uint32_t phys(uint32_t x) { return x + (x >> 4); }
 constexpr uint32_t phys_size(uint32_t n) { return n + (n >> 4) + 1; }
@@ -40,14 +42,22 @@ __host__ __device__ constexpr int rev4(int r) { return ((r & 1) << 3) | ((r & 2)
 // DIT (forward).  `lo` = the thread's local-index bits below p.  twl = per-level twiddle table for this direction.
 // x * w mod P in [0, 2P) for ANY 32-bit x, w a plain (non-Montgomery) constant with its Shoup quotient wq = floor(w 2^32 / P):
 // one IMAD.HI + two IMAD (the Montgomery form needs IMAD.WIDE + IMAD + IMAD.HI and a canonical-range operand).
-__device__ __forceinline__ uint32_t shoup_lazy(uint32_t x, uint2 w) { return x * w.x - __umulhi(x, w.y) * P; }
+// (written with an explicit mad.lo: left to itself ptxas computed q * P and x * w separately and joined them with an IMAD.IADD in two
+// thirds of the butterflies -- a third multiplier-pipe slot per product)
+__device__ __forceinline__ uint32_t shoup_lazy(uint32_t x, uint2 w) {
+  uint32_t r = x * w.x, q = __umulhi(x, w.y);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(q), "r"(0u - P));
+  return r;
+}
 
 // Values stay LAZY, in [0, 2P), between butterfly levels: each butterfly brings its two inputs below P (one VIADDMNMX
 // each), then a' = a + t and b' = a - t + P are again below 2P with no further correction -- 4 ALU + 3 multiplier-pipe
 // instructions per butterfly instead of 6 + 3.  Callers reduce once before storing (or multiply by a canonical
 // Montgomery word, which accepts a lazy operand).
+// `ones` = 0xffffffff from a launch argument: min(a + b, ones) is ONE VIADDMNMX, i.e. the butterfly's two-input addition stays
+// on the ALU pipe instead of becoming IMAD.IADD on the multiplier pipe the Shoup products use (see poseidon2.cuh).
 template <bool INV, int JLO, int JHI>
-__device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, const uint32_t lo, const uint2* __restrict__ twl) {
+__device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, const uint32_t lo, const uint2* __restrict__ twl, const uint32_t ones) {
   if (INV) {
 #pragma unroll
     for (int j = JHI - 1; j >= JLO; --j) {
@@ -56,7 +66,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
       for (int r = 0; r < 16; ++r) {
         if (r & (1 << j)) continue;
         uint32_t a = reduce_2p(v[r]), b = reduce_2p(v[r | (1 << j)]);
-        v[r] = a + b;
+        v[r] = min(a + b, ones);
         uint32_t d = a - b + P;
         if (q == 0) v[r | (1 << j)] = d;
         else v[r | (1 << j)] = shoup_lazy(d, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
@@ -72,7 +82,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
         uint32_t a = reduce_2p(v[r]), b = v[r | (1 << j)];
         if (q != 0) b = shoup_lazy(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
         b = reduce_2p(b);
-        v[r] = a + b;
+        v[r] = min(a + b, ones);
         v[r | (1 << j)] = a - b + P;
       }
     }
@@ -105,7 +115,7 @@ enum : int { EPI_NONE = 0, EPI_SCALE = 1, EPI_TABLE = 2 };
 
 // Inverse: in place.  epilogue multiplies position x of every 2^A block by table[x] (EPI_TABLE) or by `scale`.
 template <int A, int EPI>
-__global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ io, const uint2* __restrict__ twl, const uint32_t* __restrict__ table, uint32_t scale) {
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ io, const uint2* __restrict__ twl, const uint32_t* __restrict__ table, uint32_t scale, uint32_t ones) {
   __shared__ uint32_t sm[phys_size(TILE)];
   constexpr int L = 1 << A, TPB = L / 16;           // threads per sub-transform
   const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
   // first round: field [A-4, A): element r * TPB + t -> coalesced loads
 #pragma unroll
   for (int r = 0; r < 16; ++r) v[r] = base[(uint32_t)r * TPB + t];
-  radix_round<true, 0, 4>(v, P0, t, twl);
+  radix_round<true, 0, 4>(v, P0, t, twl, ones);
   int p_prev = P0;
 #pragma unroll
   for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
@@ -130,8 +140,8 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
     __syncthreads();
-    if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
-    else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
+    if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
+    else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl, ones);
     p_prev = pc;
   }
   // here p_prev == 0 (A >= 4): registers are 16 consecutive elements
@@ -141,12 +151,12 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint4 w = __ldg(tb + g);
-      v[4 * g] = mont_mul(v[4 * g], w.x); v[4 * g + 1] = mont_mul(v[4 * g + 1], w.y);
-      v[4 * g + 2] = mont_mul(v[4 * g + 2], w.z); v[4 * g + 3] = mont_mul(v[4 * g + 3], w.w);
+      v[4 * g] = mont_mul_alu(v[4 * g], w.x, ones); v[4 * g + 1] = mont_mul_alu(v[4 * g + 1], w.y, ones);
+      v[4 * g + 2] = mont_mul_alu(v[4 * g + 2], w.z, ones); v[4 * g + 3] = mont_mul_alu(v[4 * g + 3], w.w, ones);
     }
   } else if (EPI == EPI_SCALE) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = mont_mul(v[r], scale);
+    for (int r = 0; r < 16; ++r) v[r] = mont_mul_alu(v[r], scale, ones);
   } else {
     canonicalize(v);
   }
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 // Forward: out-of-place capable; EB = expand bits (0 or 2): out block element x <- in[(block_base + x) >> EB], and the
 // lowest EB levels are skipped.
 template <int A, int EB>
-__global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint2* __restrict__ twl) {
+__global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, const uint2* __restrict__ twl, uint32_t ones) {
   __shared__ uint32_t sm[phys_size(TILE)];
   constexpr int L = 1 << A, TPB = L / 16;
   const uint32_t tid = threadIdx.x, sub = tid / TPB, t = tid % TPB;
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ 
   }
   constexpr int REM = A % 4;
   constexpr int PLAST = A - 4;
-  radix_round<false, EB, 4>(v, 0, 0u, twl);
+  radix_round<false, EB, 4>(v, 0, 0u, twl, ones);
   int p_prev = 0;
 #pragma unroll
   for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
@@ -188,8 +198,8 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ 
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
     __syncthreads();
-    if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
-    else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
+    if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
+    else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
     p_prev = pc;
   }
   // p_prev == A - 4: register r is element r * TPB + t
@@ -220,7 +230,7 @@ template <int A, int TL = 0> struct STile {
 // shared by all columns and stays in L2.
 template <int A, bool INV, int TL = 0, bool TAB = false>
 __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint2* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args,
-                                                                 const uint2* __restrict__ ttab, const uint32_t* __restrict__ src) {
+                                                                 const uint2* __restrict__ ttab, const uint32_t* __restrict__ src, uint32_t ones) {
   constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
   extern __shared__ uint32_t sm[];
   const uint32_t tid = threadIdx.x;
@@ -260,8 +270,8 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
     uint32_t cur = V;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      v[rev4(m)] = mont_mul(v[rev4(m)], cur);
-      if (m != 15) cur = mont_mul(cur, g);
+      v[rev4(m)] = mont_mul_alu(v[rev4(m)], cur, ones);
+      if (m != 15) cur = mont_mul_alu(cur, g, ones);
     }
   };
 
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
     constexpr int P0 = A - 4;
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = cin[off_r + (((uint32_t)r * TPB) << s_log)];
-    radix_round<true, 0, 4>(v, P0, t, twl);
+    radix_round<true, 0, 4>(v, P0, t, twl, ones);
     int p_prev = P0;
 #pragma unroll
     for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
@@ -281,8 +291,8 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = sm[phys_tr<T_LOG>(pb_r, r, pc + T_LOG)];
       __syncthreads();
-      if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
-      else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl);
+      if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
+      else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl, ones);
       p_prev = pc;
     }
     twiddle_all(true);
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = cb[off_c + ((uint32_t)r << s_log)];
     twiddle_all(false);
-    radix_round<false, 0, 4>(v, 0, 0u, twl);
+    radix_round<false, 0, 4>(v, 0, 0u, twl, ones);
     int p_prev = 0;
 #pragma unroll
     for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
@@ -305,8 +315,8 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = sm[phys_tr<T_LOG>(pb_r, r, pc + T_LOG)];
       __syncthreads();
-      if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl);
-      else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl);
+      if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
+      else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
       p_prev = pc;
     }
     canonicalize(v);
@@ -414,7 +424,7 @@ static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, 
   size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
   auto kern = ttab ? k_ntt_s<A, INV, TL, true> : k_ntt_s<A, INV, TL, false>;
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab, src);
+  kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab, src, ntt_ones());
   launched(ctx);
 }
 static int s_tile_log() { static int v = [] { const char* e = getenv("ZKB_NTT_S_TLOG"); return e ? atoi(e) : 3; }(); return v; }
@@ -442,7 +452,7 @@ static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_lo
 template <int EPI>
 static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, const uint2* twl, const uint32_t* table, uint32_t scale) {
   unsigned grid = (unsigned)(total / TILE);
-#define ZKB_CI(AA) case AA: k_ntt_c_inv<AA, EPI><<<grid, C_THREADS, 0, ctx->stream>>>(io, twl, table, scale); break;
+#define ZKB_CI(AA) case AA: k_ntt_c_inv<AA, EPI><<<grid, C_THREADS, 0, ctx->stream>>>(io, twl, table, scale, ntt_ones()); break;
   switch (a) { ZKB_CI(4) ZKB_CI(5) ZKB_CI(6) ZKB_CI(7) ZKB_CI(8) ZKB_CI(9) ZKB_CI(10) ZKB_CI(11) ZKB_CI(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
 #undef ZKB_CI
   launched(ctx);
@@ -450,7 +460,7 @@ static void dispatch_c_inv(zkb_ctx* ctx, int a, uint32_t* io, size_t total, cons
 template <int EB>
 static void dispatch_c_fwd(zkb_ctx* ctx, int a, uint32_t* out, const uint32_t* in, size_t total, const uint2* twl) {
   unsigned grid = (unsigned)(total / TILE);
-#define ZKB_CF(AA) case AA: k_ntt_c_fwd<AA, EB><<<grid, C_THREADS, 0, ctx->stream>>>(out, in, twl); break;
+#define ZKB_CF(AA) case AA: k_ntt_c_fwd<AA, EB><<<grid, C_THREADS, 0, ctx->stream>>>(out, in, twl, ntt_ones()); break;
   switch (a) { ZKB_CF(4) ZKB_CF(5) ZKB_CF(6) ZKB_CF(7) ZKB_CF(8) ZKB_CF(9) ZKB_CF(10) ZKB_CF(11) ZKB_CF(12) default: throw Error("zkb200: unsupported contiguous NTT size"); }
 #undef ZKB_CF
   launched(ctx);

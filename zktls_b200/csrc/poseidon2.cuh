@@ -56,15 +56,7 @@ ZKB_HD uint32_t sum12(const uint32_t* s) {
 // the s-box's canonical products, the round-constant additions and the partial rounds (+6.5 % permutations/s); the
 // external linear layer is left to ptxas -- forcing its 128 additions per round onto the ALU pipe overloads it (-9 %).
 // Measurements: tools/ubench/p2_alu_adds.cu, profiles/r1_r_ubench_p2_alu_adds.txt.  On the host `ones` is a constant.
-ZKB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
-ZKB_HD uint32_t add_alu(uint32_t a, uint32_t b, uint32_t ones) { return umin32(a + b, ones); }
-ZKB_HD uint32_t mont_mul_alu(uint32_t a, uint32_t b, uint32_t ones) {      // mont_mul with the final subtraction on the ALU pipe
-  uint64_t t = (uint64_t)a * b;
-  uint32_t m = (uint32_t)t * P_INV;
-  uint32_t r = umin32((uint32_t)(t >> 32) - mul_hi32(m, P), ones);
-  uint32_t y = r + P;
-  return y < r ? y : r;
-}
+// (add_alu / mont_mul_alu live in field.cuh: the NTT butterflies use them too.)
 ZKB_HD uint32_t sbox7(uint32_t x, uint32_t ones = 0xffffffffu) {
   uint32_t x2 = mont_mul_alu(x, x, ones);
   uint32_t x4 = mont_mul_lazy(x2, x2);     // < 2P
