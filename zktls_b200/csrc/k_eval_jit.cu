@@ -118,45 +118,7 @@ __device__ __forceinline__ u32 fin(u64 a) { a = fixhi(a); u32 m = (u32)a * 0x880
 __device__ __forceinline__ void st(u32* p, u32 v) { *p = v; }
 )";
 
-// Several consecutive rows per thread (ROWS = 2 or 4): every tap is one 64 / 128-bit load, a tap `back` rows behind is a
-// neighbouring lane's vector (warp shuffle; only the first lanes of a warp load), and the per-row code is replicated
-// through overloads of the scalar helpers.  Values that do not depend on a tap (constants, globals) stay scalar.
-static std::string preamble_rows(int rows) {
-  const char* f[4] = {"x", "y", "z", "w"};
-  std::ostringstream o;
-  auto each = [&](const std::string& pat) {       // pat with '#' = field name, joined by spaces
-    std::string out;
-    for (int i = 0; i < rows; ++i) { std::string t = pat; size_t k; while ((k = t.find('#')) != std::string::npos) t.replace(k, 1, f[i]); out += t + " "; }
-    return out;
-  };
-  std::string fields; for (int i = 0; i < rows; ++i) fields += std::string(i ? ", " : "") + f[i];
-  o << "struct FV { u32 " << fields << "; };\nstruct AV { u64 " << fields << "; };\n";
-  for (const char* name : {"add", "sub", "mul"}) {
-    o << "__device__ __forceinline__ FV " << name << "(FV a, FV b) { FV r; " << each(std::string("r.# = ") + name + "(a.#, b.#);") << "return r; }\n";
-    o << "__device__ __forceinline__ FV " << name << "(FV a, u32 b) { FV r; " << each(std::string("r.# = ") + name + "(a.#, b);") << "return r; }\n";
-    o << "__device__ __forceinline__ FV " << name << "(u32 a, FV b) { FV r; " << each(std::string("r.# = ") + name + "(a, b.#);") << "return r; }\n";
-  }
-  o << "__device__ __forceinline__ AV wide(FV f, u32 w) { AV r; " << each("r.# = wide(f.#, w);") << "return r; }\n"
-    << "__device__ __forceinline__ AV widem(FV m, FV f, u32 w) { AV r; " << each("r.# = widem(m.#, f.#, w);") << "return r; }\n"
-    << "__device__ __forceinline__ AV widem(FV m, u32 f, u32 w) { AV r; " << each("r.# = widem(m.#, f, w);") << "return r; }\n"
-    << "__device__ __forceinline__ void wacc(AV& a, FV f, u32 w) { " << each("wacc(a.#, f.#, w);") << "}\n"
-    << "__device__ __forceinline__ void wacc(AV& a, u32 f, u32 w) { " << each("wacc(a.#, f, w);") << "}\n"
-    << "__device__ __forceinline__ AV fixhi(AV a) { AV r; " << each("r.# = fixhi(a.#);") << "return r; }\n"
-    << "__device__ __forceinline__ FV fin(AV a) { FV r; " << each("r.# = fin(a.#);") << "return r; }\n"
-    << "__device__ __forceinline__ AV W0(FV f, u32 w) { return wide(f, w); }\n"
-    << "__device__ __forceinline__ AV W0(u32 f, u32 w) { AV r; " << each("r.# = wide(f, w);") << "return r; }\n";
-  const char* vt = rows == 4 ? "uint4" : "uint2";
-  o << "__device__ __forceinline__ FV ldv(const u32* p) { const " << vt << " v = __ldg(reinterpret_cast<const " << vt << "*>(p)); FV r; " << each("r.# = v.#;") << "return r; }\n"
-    << "__device__ __forceinline__ void st(u32* p, FV v) { *reinterpret_cast<" << vt << "*>(p) = make_" << vt << "(" ;
-  for (int i = 0; i < rows; ++i) o << (i ? ", " : "") << "v." << f[i];
-  o << "); }\n"
-    // rows (c - 4 back ..) of a column: this thread's vector v0 of rows (c ..) moved up by 4 back / ROWS lanes; `p` = the direct address
-    << "__device__ __forceinline__ FV tap_shfl(FV v0, const u32* p, u32 lanes) {\n  FV r; " << each("r.# = __shfl_up_sync(0xffffffffu, v0.#, lanes);")
-    << "\n  if ((threadIdx.x & 31u) < lanes) r = ldv(p);\n  return r;\n}\n";
-  return o.str();
-}
-
-// Fp4 arithmetic over a component type T (u32: one row; FV: four rows); the second operand of mul4 is a power of poly_mix
+// Fp4 arithmetic over a component type T (u32 here; the helpers are generic); the second operand of mul4 is a power of poly_mix
 const char* PREAMBLE_F4 = R"(
 template <class T> struct F4T { T a, b, c, d; };
 typedef F4T<u32> F4;
@@ -186,7 +148,7 @@ struct EvalJitKernel {
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   uint32_t n_powers = 1;
-  int rows = 1, block = 128;      // domain points per thread, threads per CTA
+  int block = 128;                // threads per CTA (one domain point per thread)
   size_t smem = 0;                // dynamic shared memory per CTA
   CUdeviceptr cdata = 0;        // __constant__ zkb_cd (per-proof powers + globals) when the circuit's data fits in 64 KB
   size_t cdata_bytes = 0;
@@ -196,22 +158,18 @@ struct EvalJitCache {
   std::map<uint64_t, bool> failed;
 };
 
-static int min_blocks(int rows);
-// rows per thread: 4 (vectorised) unless ZKB_EC_ROWS = 1
-// Measured on B200 (SYN-280, 2^22 domain points; profiles/r1_l_ec_variants.txt): one row per thread with indexed tap
-// addresses 2.5 ms; row pointers + uniform column offsets 2.7 ms; 2 rows per thread 3.7-4.1 ms; 4 rows per thread
-// 2.6-5.0 ms (the 16 64-bit accumulators spill) -- so ZKB_EC_ROWS = 1 and ZKB_EC_PTR = 0 are the defaults.
-static int ec_rows() { const char* e = getenv("ZKB_EC_ROWS"); int v = e ? atoi(e) : 1; return v == 2 || v == 4 ? v : 1; }
-static bool ec_ptr() { const char* e = getenv("ZKB_EC_PTR"); return e && atoi(e) != 0; }
-static uint32_t ec_batch(int rows) { const char* e = getenv("ZKB_EC_BATCH"); int v = e ? atoi(e) : (rows == 4 ? 1 : rows == 2 ? 2 : 4); return (uint32_t)(v < 1 ? 1 : v > 4096 ? 4096 : v); }
+static int min_blocks();
+// Variants of the register form that were measured on B200 and removed again (SYN-280, 2^22 points; profiles/r1_l_ec_variants.txt):
+// 2 / 4 rows per thread with 64 / 128-bit tap loads and the `back` tap taken from the neighbouring lane by shuffle: 2.6-5.0 ms (the
+// 64-bit accumulators of 4 rows spill); per-thread row pointers + uniform column offsets: 2.7 ms; this form: 2.4-2.5 ms.
+static uint32_t ec_batch() { const char* e = getenv("ZKB_EC_BATCH"); int v = e ? atoi(e) : 4; return (uint32_t)(v < 1 ? 1 : v > 4096 ? 4096 : v); }
 static uint32_t ec_prefetch() { const char* e = getenv("ZKB_EC_PREFETCH"); int v = e ? atoi(e) : 1; return (uint32_t)(v < 0 ? 0 : v > 8 ? 8 : v); }
 // Per-proof kernel data: [powers of poly_mix, 4 words each][mix globals][out globals].  It lives in the module's
 // __constant__ bank when it fits (operands then come straight from the constant cache), else behind a pointer.
 constexpr size_t CONST_WORDS_MAX = 15 * 1024;
 static bool const_mode(const CircuitDef& c, uint32_t n_powers) { return 4 * (size_t)n_powers + c.mix_size + c.out_size <= CONST_WORDS_MAX; }
 
-// Straight-line source for the circuit.  n_powers = number of poly_mix powers the kernel reads; rows = domain points per
-// thread (1, or 2 / 4 = vectorised form, see preamble_rows).
+// Straight-line source for the circuit (one domain point per thread); gi.n_powers = number of poly_mix powers the kernel reads.
 // Liveness and mix-power bookkeeping shared by the generators.
 struct Analysis {
   std::vector<char> fp_used, mx_used;
@@ -259,7 +217,6 @@ static Analysis analyse(const CircuitDef& c) {
 constexpr int SG_BLOCK = 256;
 struct GenInfo {
   uint32_t n_powers = 1;
-  int rows = 1;              // domain points per thread
   int block = JIT_BLOCK;     // threads per CTA
   size_t smem = 0;           // dynamic shared memory (staged form)
   bool staged = false;
@@ -286,13 +243,11 @@ __device__ __forceinline__ void copy_col(u32* dst, const u32* col, u32 c0, u32 m
 }
 )";
 
-static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool staged) {
+static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
   const size_t n = c.steps.size();
-  if (staged) rows = 1;
-  const bool vec = rows > 1;
   const Analysis A = analyse(c);
   uint32_t& n_powers = gi.n_powers;
-  gi.rows = rows; gi.block = JIT_BLOCK; gi.smem = 0; gi.staged = false;
+  gi.block = JIT_BLOCK; gi.smem = 0; gi.staged = false;
   const std::vector<char>&fp_used = A.fp_used, &mx_used = A.mx_used;
   const std::vector<uint32_t>&fp_of = A.fp_of, &eqz_uses = A.eqz_uses, &other_uses = A.other_uses, &mx_pow = A.mx_pow;
   n_powers = A.n_powers;
@@ -343,8 +298,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
   std::ostringstream o;
   o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
   if (staged) o << "#define HALO " << halo << "u\n#define BLOCK " << SG_BLOCK << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
-  if (vec) o << preamble_rows(rows) << "typedef FV RV; typedef AV ACC;\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) ldv(p)\n";
-  else o << "typedef u32 RV; typedef u64 ACC;\n#define W0(f, w) wide(f, w)\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) __ldg(p)\n";
+  o << "typedef u32 RV; typedef u64 ACC;\n#define W0(f, w) wide(f, w)\n#define WM(m, f, w) widem(m, f, w)\n#define LD(p) __ldg(p)\n";
   o << PREAMBLE_F4 << "typedef F4T<RV> MV;\n";
   if (cm) {
     o << "__constant__ u32 zkb_cd[" << std::max<size_t>(gl_off + c.mix_size + c.out_size, 4) << "];\n"
@@ -353,12 +307,12 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
   } else {
     o << "#define PW(k) __ldg(pw + (k))\n#define GL(i) __ldg(gl + (i))\n";
   }
-  const int ctas_per_sm = staged ? (int)std::max<size_t>(1, std::min<size_t>(env_u32("ZKB_EC_MINBLOCKS", 8, 1, 16), (220 * 1024) / (gi.smem + 1024))) : min_blocks(rows);
+  const int ctas_per_sm = staged ? (int)std::max<size_t>(1, std::min<size_t>(env_u32("ZKB_EC_MINBLOCKS", 8, 1, 16), (220 * 1024) / (gi.smem + 1024))) : min_blocks();
   o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", " << ctas_per_sm << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
        << (staged ? "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));     // opaque: see the note on uniform address arithmetic below\n"
                   : "  const size_t dom = (size_t)mask + 1;\n")
-       << "  const u32 c = (blockIdx.x * " << gi.block << "u + threadIdx.x) * " << rows << "u;\n";
+       << "  const u32 c = blockIdx.x * " << gi.block << "u + threadIdx.x;\n";
   // producer code of one block: expect the bytes, then one bulk copy per column (issued by thread 0 only)
   auto issue_block = [&](uint32_t b) {
     const uint32_t st = b % stages;
@@ -406,19 +360,9 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
     a << "sp[" << slot_words - 4 * (long)t.back << "]";
     return a.str();
   };
-  // Tap addresses: one per-thread row pointer for every (group, back) pair in use, plus the CTA-uniform column offset
-  // col * dom -- the per-tap address arithmetic then runs on the uniform datapath / ALU instead of one IMAD.WIDE per load
-  // on the multiplier pipe (ZKB_EC_PTR=0 restores the indexed form).
-  const bool ptr_mode = ec_ptr();
-  if (ptr_mode) {
-    std::set<std::pair<uint32_t, uint32_t>> gb;
-    for (const TapDef& t : c.taps) gb.insert({t.group, t.back});
-    for (auto& e : gb) o << "  const u32* const rp" << e.first << "_" << e.second << " = g" << e.first << " + ((c - " << 4 * e.second << "u) & mask);\n";
-  }
   auto tap_addr = [&](const TapDef& t) {
     std::ostringstream a;
-    if (ptr_mode) a << "rp" << t.group << "_" << t.back << " + (size_t)" << t.column << " * dom";
-    else a << "g" << t.group << " + (size_t)" << t.column << " * dom + ((c - " << 4 * t.back << "u) & mask)";
+    a << "g" << t.group << " + (size_t)" << t.column << " * dom + ((c - " << 4 * t.back << "u) & mask)";
     return a.str();
   };
   enum { ST_ZERO = 0, ST_CANON = 1, ST_ACC = 2 };
@@ -432,7 +376,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
   // Load scheduling.  The kernel is bound by global-load latency (ncu: 87 % long-scoreboard stalls when every tap is loaded
   // right before its use), so the tap loads of the next `batch` constraints are hoisted in front of the arithmetic of the
   // current ones (software pipelining, distance `prefetch` batches); a tap needed twice within the hoisted group is loaded once.
-  const uint32_t batch = ec_batch(rows), prefetch = ec_prefetch();
+  const uint32_t batch = ec_batch(), prefetch = ec_prefetch();
   std::vector<uint32_t> get_batch(n, 0);
   uint32_t n_batches = 1;
   {
@@ -450,25 +394,14 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
   std::vector<char> get_done(n, 0);
   auto hoist = [&](uint32_t b) {
     if (b >= gets_of.size()) return;
-    std::map<uint32_t, uint32_t> seen;                           // tap -> fp id, within this group
-    std::map<std::pair<uint32_t, uint32_t>, uint32_t> row0;      // (group, column) -> fp id of its back-0 tap, within this group
-    // back-0 taps first, so that a tap further back of the same column can take them from the neighbouring lanes
-    for (int pass = 0; pass < 2; ++pass)
-      for (size_t i : gets_of[b]) {
-        const StepDef& s = c.steps[i];
-        const TapDef& t = c.taps[s.a];
-        if ((t.back == 0) != (pass == 0)) continue;
-        auto it = seen.find(s.a);
-        if (it != seen.end()) { o << "  const RV f" << fp_of[i] << " = f" << it->second << ";\n"; }
-        else {
-          auto r0 = row0.find({t.group, t.column});
-          if (vec && t.back > 0 && 4 * t.back / rows < 32 && r0 != row0.end()) o << "  const RV f" << fp_of[i] << " = tap_shfl(f" << r0->second << ", " << tap_addr(t) << ", " << 4 * t.back / rows << "u);\n";
-          else o << "  const RV f" << fp_of[i] << " = LD(" << tap_addr(t) << ");\n";
-          seen[s.a] = fp_of[i];
-          if (t.back == 0) row0[{t.group, t.column}] = fp_of[i];
-        }
-        get_done[i] = 1;
-      }
+    std::map<uint32_t, uint32_t> seen;       // tap -> fp id, within this group
+    for (size_t i : gets_of[b]) {
+      const StepDef& s = c.steps[i];
+      auto it = seen.find(s.a);
+      if (it != seen.end()) { o << "  const RV f" << fp_of[i] << " = f" << it->second << ";\n"; }
+      else { o << "  const RV f" << fp_of[i] << " = LD(" << tap_addr(c.taps[s.a]) << ");\n"; seen[s.a] = fp_of[i]; }
+      get_done[i] = 1;
+    }
   };
   uint32_t hoisted_upto = 0;                  // batches [0, hoisted_upto) have had their loads emitted
   auto hoist_until = [&](uint32_t b_end) { while (hoisted_upto < b_end && hoisted_upto < gets_of.size()) hoist(hoisted_upto++); };
@@ -541,9 +474,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, int rows, bool sta
     o << ";\n";
     state[id] = ST_CANON;
   }
-  if (rows == 4) o << "  FV den; den.x = invden.x; den.y = invden.y; den.z = invden.z; den.w = invden.w;     // rows c .. c + 3: c is a multiple of 4\n";
-  else if (rows == 2) o << "  FV den; den.x = (c & 2u) ? invden.z : invden.x; den.y = (c & 2u) ? invden.w : invden.y;     // rows c, c + 1: c is even\n";
-  else o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
+  o << "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n";
   if (state[c.ret] == ST_ZERO) o << "  MV r; r.a = r.b = r.c = r.d = sub(den, den);\n";
   else o << "  const MV r = scale4(m" << c.ret << ", den);\n";
   o << "  st(check + c, r.a); st(check + dom + c, r.b); st(check + 2 * dom + c, r.c); st(check + 3 * dom + c, r.d);\n}\n";
@@ -566,7 +497,7 @@ static std::string cache_dir() {
   }
   return "/tmp/zkb200-cache";
 }
-static int min_blocks(int rows) { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : (rows == 4 ? 4 : rows == 2 ? 6 : 8); return v < 1 ? 1 : v > 16 ? 16 : v; }
+static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : v > 16 ? 16 : v; }
 
 static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
   Api& a = api();
@@ -607,8 +538,8 @@ void eval_jit_free(zkb_ctx* ctx) {
 // The generated source (for tests / inspection) -- no device needed.
 std::string eval_jit_source(const CircuitDef& c) {
   GenInfo gi;
-  if (ec_staged()) { std::string src = generate(c, gi, 1, true); if (!src.empty()) return src; }
-  return generate(c, gi, ec_rows(), false);
+  if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty()) return src; }
+  return generate(c, gi, false);
 }
 // Compiles the source with NVRTC without loading it (CPU-only check that the generator emits valid CUDA).
 bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
@@ -616,19 +547,18 @@ bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
   if (!a.ok) { why = a.why; return false; }
   std::vector<char> cubin; GenInfo gi;
   // every form a proof may use: the staged kernel, and the register form used for tiny domains / unaligned sub-buffers
-  if (ec_staged()) { std::string src = generate(c, gi, 1, true); if (!src.empty() && !compile(src, cubin, why)) return false; }
-  if (ec_rows() > 1 && !compile(generate(c, gi, ec_rows(), false), cubin, why)) return false;
-  return compile(generate(c, gi, 1, false), cubin, why);
+  if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty() && !compile(src, cubin, why)) return false; }
+  return compile(generate(c, gi, false), cubin, why);
 }
 
-static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, int rows, bool staged, std::string& why) {
+static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool staged, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return nullptr; }
   if (!a.cu_ok) { why = a.cu_why; return nullptr; }
   if (!ctx->jit) ctx->jit = new EvalJitCache();
   EvalJitCache* cache = (EvalJitCache*)ctx->jit;
   GenInfo gi;
-  std::string src = generate(c, gi, rows, staged);
+  std::string src = generate(c, gi, staged);
   if (src.empty()) { why = "circuit does not fit the staged form"; return nullptr; }
   const uint32_t np = gi.n_powers;
   uint64_t key = fnv1a(src);
@@ -636,7 +566,7 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, int ro
   if (it != cache->kernels.end()) return &it->second;
   if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return nullptr; }
   std::vector<char> cubin;
-  EvalJitKernel k; k.n_powers = np; k.rows = gi.rows; k.block = gi.block; k.smem = gi.smem;
+  EvalJitKernel k; k.n_powers = np; k.block = gi.block; k.smem = gi.smem;
   if (!compile(src, cubin, why)) { cache->failed[key] = true; return nullptr; }
   ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
@@ -655,19 +585,15 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
                     const Fp4& poly_mix, int po2, std::string& why) {
   const size_t n = (size_t)1 << po2, domain = n * INV_RATE;
   if (domain < (size_t)JIT_BLOCK) { why = "domain smaller than one block"; return false; }
-  // four rows per thread need 128-bit aligned columns (always true for pool allocations; a caller's sub-buffer view may not be)
-  int rows = ec_rows();
   bool aligned = ((uintptr_t)d_check & 15) == 0;
   for (int g = 0; g < 3; ++g) if ((uintptr_t)d_groups[g] & 15) aligned = false;
-  if (domain < (size_t)JIT_BLOCK * rows || !aligned) rows = 1;
   const EvalJitKernel* k = nullptr;
-  if (ec_staged() && aligned && domain >= (size_t)SG_BLOCK) {       // bulk copies need 16-byte aligned columns
+  if (ec_staged() && aligned && domain >= (size_t)SG_BLOCK) {       // bulk copies need 16-byte aligned columns (pool allocations are; a caller's sub-buffer view may not be)
     std::string why_staged;
-    k = get_kernel(ctx, c, 1, true, why_staged);
+    k = get_kernel(ctx, c, true, why_staged);
   }
-  if (!k) k = get_kernel(ctx, c, rows, false, why);
+  if (!k) k = get_kernel(ctx, c, false, why);
   if (!k) return false;
-  rows = k->rows;
   // per-proof data: [powers of poly_mix (4 words each)] [mix globals] [out globals]
   std::vector<uint32_t> h(4 * (size_t)k->n_powers + c.mix_size + c.out_size + 4);
   Fp4 cur = Fp4::one();
@@ -694,7 +620,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   const uint4* pw = (const uint4*)d_data; const uint32_t* d_gl = d_data + 4 * (size_t)k->n_powers;
   uint32_t mask = (uint32_t)(domain - 1);
   void* args[] = {&d_check, &g0, &g1, &g2, &pw, &d_gl, &invden, &mask};
-  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / ((size_t)k->block * rows)), 1, 1, (unsigned)k->block, 1, 1, (unsigned)k->smem, (CUstream)ctx->stream, args, nullptr);
+  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / (size_t)k->block), 1, 1, (unsigned)k->block, 1, 1, (unsigned)k->smem, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
   if (d_data) pool_free(ctx, d_data);
