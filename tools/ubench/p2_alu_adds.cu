@@ -161,6 +161,10 @@ template <int W> __device__ __forceinline__ void permute_w(uint32_t* s, uint32_t
 // VIADDMNMX additions (4 ALU instructions instead of 1 IMAD) in the first NM products of every s-box.
 template <int ON> __device__ __forceinline__ uint32_t m_sel(uint32_t lo, uint32_t ones) {
   if (!ON) return lo * P_INV;
+  if (ON == 2) {      // (lo << 27) + (lo << 31) == ((lo ^ (lo << 4)) << 27) mod 2^32: an XOR that ptxas cannot re-fuse into an IMAD
+    uint32_t k = (lo ^ (lo << 4)) << 27;
+    return min(lo + k, ones);
+  }
   uint32_t s1 = min(lo + (lo << 27), ones);
   return min(s1 + (lo << 31), ones);
 }
@@ -177,8 +181,9 @@ template <int ON> __device__ __forceinline__ uint32_t mmx_lazy(uint32_t a, uint3
   return (uint32_t)(t >> 32) - mul_hi32(m, P) + P;
 }
 template <int NM> __device__ __forceinline__ uint32_t sboxx(uint32_t x, uint32_t ones) {
-  uint32_t x2 = mmx_canon<(NM >= 1)>(x, x, ones), x4 = mmx_lazy<(NM >= 2)>(x2, x2, ones), x6 = mmx_lazy<(NM >= 3)>(x4, x2, ones);
-  return mmx_canon<(NM >= 4)>(x6, x, ones);
+  constexpr int K = NM >= 10 ? 2 : 1, N = NM % 10;      // NM = 1x: the XOR form of m
+  uint32_t x2 = mmx_canon<(N >= 1 ? K : 0)>(x, x, ones), x4 = mmx_lazy<(N >= 2 ? K : 0)>(x2, x2, ones), x6 = mmx_lazy<(N >= 3 ? K : 0)>(x4, x2, ones);
+  return mmx_canon<(N >= 4 ? K : 0)>(x6, x, ones);
 }
 template <int NM> __device__ __forceinline__ void permute_x(uint32_t* s, uint32_t o) {
   const auto& T = ZKB_P2_TABLES;
@@ -264,6 +269,10 @@ int main(int argc, char** argv) {
     run<2002, 256>("x2 = w11 + shift-add m in 2 of 4 products");
     run<2003, 256>("x3 = w11 + shift-add m in 3 of 4 products");
     run<2004, 256>("x4 = w11 + shift-add m in 4 of 4 products");
+    run<2011, 256>("y1 = w11 + xor-shift m in 1 of 4 products");
+    run<2012, 256>("y2 = w11 + xor-shift m in 2 of 4 products");
+    run<2013, 256>("y3 = w11 + xor-shift m in 3 of 4 products");
+    run<2014, 256>("y4 = w11 + xor-shift m in 4 of 4 products");
     if (argc > 2) return 0;
     run<1011 + 16 * 1, 256>("w11 + the 4x4 blocks");
     run<1011 + 16 * 2, 256>("w11 + column sums");
