@@ -14,33 +14,28 @@ constexpr int HASH_BLOCK = 128;
 static inline uint32_t p2_ones() { return 0xffffffffu; }
 
 // out[r] = unpadded_hash(matrix[0*rows + r], matrix[1*rows + r], ...)   (rate 16, overwrite mode, zero pad)
-// Grid-stride over row blocks: with the default grid (one CTA per 256 rows) every CTA does one trip; hash_rows() may instead launch a
-// PERSISTENT grid of k CTAs per SM (ZKB_HASH_CTAS_PER_SM), which leaves registers free for a second, ALU/LSU-bound kernel of another
-// segment in flight to share the SMs (the permutation saturates the fmaheavy pipe with five 256-thread CTAs just as well as with six).
-template <int BLOCK, bool PERSIST = false>
+template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_hash_rows(uint32_t* __restrict__ out, const uint32_t* __restrict__ matrix, size_t rows, uint32_t cols, uint32_t ones) {
-  const uint32_t stride = PERSIST ? gridDim.x * BLOCK : 0u;
-  for (size_t r = (size_t)blockIdx.x * BLOCK + threadIdx.x; r < rows; r += stride) {
-    uint32_t s[24];
+  size_t r = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (r >= rows) return;
+  uint32_t s[24];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) s[i] = 0;
-    const uint32_t* p = matrix + r;
-    uint32_t c = 0;
-    for (; c + 16 <= cols; c += 16) {
+  for (int i = 0; i < 24; ++i) s[i] = 0;
+  const uint32_t* p = matrix + r;
+  uint32_t c = 0;
+  for (; c + 16 <= cols; c += 16) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) s[i] = __ldg(p + (size_t)(c + i) * rows);
-      p2::permute(s, ZKB_P2_TABLES, ones);
-    }
-    if (c < cols || cols == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) s[i] = (c + i < cols) ? __ldg(p + (size_t)(c + i) * rows) : 0u;
-      p2::permute(s, ZKB_P2_TABLES, ones);
-    }
-    uint4* o = reinterpret_cast<uint4*>(out + r * 8);
-    o[0] = make_uint4(s[0], s[1], s[2], s[3]);
-    o[1] = make_uint4(s[4], s[5], s[6], s[7]);
-    if (!PERSIST) break;
+    for (int i = 0; i < 16; ++i) s[i] = __ldg(p + (size_t)(c + i) * rows);
+    p2::permute(s, ZKB_P2_TABLES, ones);
   }
+  if (c < cols || cols == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = (c + i < cols) ? __ldg(p + (size_t)(c + i) * rows) : 0u;
+    p2::permute(s, ZKB_P2_TABLES, ones);
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + r * 8);
+  o[0] = make_uint4(s[0], s[1], s[2], s[3]);
+  o[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
 // nodes[out_base + i] = hash_pair(nodes[in_base + 2i], nodes[in_base + 2i + 1]); digests are 8 words.
@@ -75,17 +70,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_merkle_tail(uint32_t* __restri
 
 void hash_rows(zkb_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows, size_t cols) {
   if (rows == 0) return;
-  static int block = [] { const char* e = getenv("ZKB_HASH_BLOCK"); int v = e ? atoi(e) : 256; return v == 64 || v == 128 ? v : 256; }();
-  static int per_sm = [] { const char* e = getenv("ZKB_HASH_CTAS_PER_SM"); return e ? atoi(e) : 0; }();      // 0: one CTA per row block
-  unsigned grid = grid_for(rows, per_sm > 0 ? 256u : (unsigned)block);
-  if (per_sm > 0) {
-    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid = std::min<unsigned>(grid, (unsigned)(sms * per_sm));
-  }
-  if (per_sm > 0) k_hash_rows<256, true><<<grid, 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
-  else if (block == 256) k_hash_rows<256><<<grid, 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
-  else if (block == 64) k_hash_rows<64><<<grid, 64, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
-  else k_hash_rows<128><<<grid, 128, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
+  static int block = [] { const char* e = getenv("ZKB_HASH_BLOCK"); return e ? atoi(e) : 256; }();
+  if (block == 256) k_hash_rows<256><<<grid_for(rows, 256), 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
+  else if (block == 64) k_hash_rows<64><<<grid_for(rows, 64), 64, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
+  else if (block == 128) k_hash_rows<128><<<grid_for(rows, 128), 128, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
+  else k_hash_rows<256><<<grid_for(rows, 256), 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
   launched(ctx);
 }
 void hash_fold(zkb_ctx* ctx, uint32_t* nodes, size_t input_size, size_t output_size) {
