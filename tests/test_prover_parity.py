@@ -139,3 +139,68 @@ def test_full_size_segment_verifies(hal):
     with pytest.raises(ZkbError):
         verify_segment(blob, gp.finish(accum_m))
     gp.close()
+
+
+def _deep_tap_circuit(accum_cols=3, code_cols=4, data_cols=21, mix_size=3, out_size=2):
+    """A circuit the SYN family does not cover: taps up to 5 rows back (a 20-row halo in the staged eval_check), columns that are
+    read by many constraints (resident) next to columns read once (streamed), nested AndCond blocks and a constraint on globals only."""
+    from zktls_b200.circuit import CircuitBuilder, GROUP_ACCUM, GROUP_CODE, GROUP_DATA, GLOBAL_MIX, GLOBAL_OUT
+    b = CircuitBuilder(accum_cols, code_cols, data_cols, mix_size, out_size, info=b"DEEPTAPS:v1_____")
+    backs = {GROUP_ACCUM: (0, 1, 3), GROUP_CODE: (0, 2), GROUP_DATA: (0, 1, 2, 5)}
+    for g, n in ((GROUP_ACCUM, accum_cols), (GROUP_CODE, code_cols), (GROUP_DATA, data_cols)):
+        for c in range(n):
+            for k in backs[g]:
+                b.add_tap(g, c, k)
+    b.finish_taps()
+    sel, gate = b.get(GROUP_CODE, 0, 0), b.get(GROUP_CODE, 1, 2)
+    top = b.and_eqz(b.true(), b.mul(b.get_global(GLOBAL_MIX, 0), b.sub(b.get_global(GLOBAL_OUT, 1), b.const(7))))      # globals only
+    inner = b.true()
+    for j in range(data_cols):
+        cur, p2_, p5 = b.get(GROUP_DATA, j, 0), b.get(GROUP_DATA, (j + 3) % data_cols, 2), b.get(GROUP_DATA, j, 5)
+        k = b.get(GROUP_CODE, 2 + j % (code_cols - 2), 0)
+        inner = b.and_eqz(inner, b.sub(b.sub(cur, b.mul(p2_, p5)), b.mul(k, b.get(GROUP_DATA, j, 1))))
+    deeper = b.true()
+    for j in range(accum_cols):
+        a0, a3 = b.get(GROUP_ACCUM, j, 0), b.get(GROUP_ACCUM, j, 3)
+        deeper = b.and_eqz(deeper, b.sub(b.add(a0, b.get(GROUP_ACCUM, (j + 1) % accum_cols, 1)), b.mul(a3, b.get_global(GLOBAL_MIX, j % mix_size))))
+    inner = b.and_cond(inner, gate, deeper)
+    b.ret = b.and_cond(top, sel, inner)
+    return b
+
+
+@pytest.mark.parametrize("po2,env", [(6, {}), (8, {}), (8, {"ZKB_EC_STAGES": "2", "ZKB_EC_CPS": "1"}), (8, {"ZKB_EC_RES": "0", "ZKB_EC_CPS": "3"}),
+                                     (9, {"ZKB_EC_STAGES": "5", "ZKB_EC_CPS": "2", "ZKB_EC_RES_USES": "2"}), (8, {"ZKB_EC_STAGED": "0"}), (7, {"ZKB_EVAL_CHECK": "vm"})])
+def test_eval_check_deep_taps_every_form(hal, oracle, po2, env, monkeypatch):
+    """eval_check against the oracle on a circuit with a 20-row halo, in the staged form under several ring shapes (one column per
+    stage, no resident columns, everything resident), in the register form, and in the device interpreter."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b = _deep_tap_circuit()
+    blob = b.blob()
+    rng = np.random.default_rng(100 + po2)
+    dom = 4 << po2
+    accum, code, data = (oracle.random_fp(rng, n * dom) for n in b.group_size)
+    mix, out, pm = oracle.random_fp(rng, b.mix_size), oracle.random_fp(rng, b.out_size), oracle.random_fp(rng, 4)
+    chk = hal.alloc_elem(4 * dom)
+    hal.eval_check(chk, blob, hal.copy_from_elem(accum), hal.copy_from_elem(code), hal.copy_from_elem(data), mix, out, pm, po2)
+    assert np.array_equal(chk.to_numpy(), oracle.eval_check(blob, accum, code, data, mix, out, pm, po2))
+
+
+def test_eval_check_below_the_minimum_domain_is_an_error_string(hal, oracle):
+    from zktls_b200 import ZkbError
+    b = _deep_tap_circuit(); dom = 4 << 4
+    bufs = [hal.alloc_elem(max(n * dom, 4)) for n in b.group_size]
+    with pytest.raises(ZkbError, match="po2 >= 6"):
+        hal.eval_check(hal.alloc_elem(4 * dom), b.blob(), *bufs, np.zeros(b.mix_size, np.uint32), np.zeros(b.out_size, np.uint32), np.ones(4, np.uint32), 4)
+
+
+def test_device_traces_are_left_untouched_by_the_prover(hal):
+    """The first iNTT pass reads a device-resident trace in place (no copy): the caller's buffers must come back unchanged."""
+    from zktls_b200.prover import SegmentProver
+    for shape, po2 in ((SMALL, 10), (MID, 13)):      # 13: the tiled (out-of-place) path; 10: contiguous-only plan (copy first)
+        blob = circuit.syn_circuit(**shape).blob()
+        io, code_m, data_m, accum_m = synth.trace_a(shape, po2, 77)
+        bufs = [hal.copy_from_elem(t) for t in (code_m, data_m, accum_m)]
+        p = SegmentProver(hal, blob); p.prove(po2, io, *bufs); p.close()
+        for b_, t in zip(bufs, (code_m, data_m, accum_m)):
+            assert np.array_equal(b_.to_numpy(), t)
