@@ -138,32 +138,58 @@ __global__ void k_mix_powers(uint4* __restrict__ pw, Fp4Arg start, Fp4Arg mix, u
   Fp4 r = arg4(start) * pow(arg4(mix), i);
   pw[i] = st4(r);
 }
-// grid.y = combo id; each thread owns out[combo][idx] and sweeps the columns that map to this combo.
+// grid.y = combo id; each thread owns out[combo][idx] and sweeps the columns that map to this combo.  Per chunk of 256 columns warp 0
+// compacts the matching column indices into shared memory, so the sweep is branch-free and keeps four coefficient loads in flight
+// per thread.  (That alone changed nothing -- see k_mix_poly_coeffs4 below for what did; this form remains for counts that are not a multiple of 4.)
 constexpr int MIX_CHUNK = 256;
 __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict__ out, const uint4* __restrict__ pw, const uint32_t* __restrict__ in,
                                                                const uint32_t* __restrict__ combos, uint32_t input_size, size_t count) {
   __shared__ uint4 s_pw[MIX_CHUNK];
   __shared__ uint32_t s_combo[MIX_CHUNK];
-  const uint32_t combo = blockIdx.y;
+  __shared__ uint16_t s_list[MIX_CHUNK + 4];
+  __shared__ uint32_t s_hits;
+  const uint32_t combo = blockIdx.y, lane = threadIdx.x & 31;
   size_t idx = (size_t)blockIdx.x * EW_BLOCK + threadIdx.x;
   bool live = idx < count;
   // lazy 64-bit accumulation (see fixhi): one IMAD.WIDE per column and Fp4 component, one high-word fix per two columns
   uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  uint32_t terms = 0;
   bool any = false;
   for (uint32_t base = 0; base < input_size; base += MIX_CHUNK) {
     uint32_t chunk = min((uint32_t)MIX_CHUNK, input_size - base);
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < chunk; t += EW_BLOCK) { s_pw[t] = pw[base + t]; s_combo[t] = combos[base + t]; }
     __syncthreads();
-    if (!live) continue;
-    for (uint32_t t = 0; t < chunk; ++t) {
-      if (s_combo[t] != combo) continue;      // uniform across the block
-      uint4 p = s_pw[t];
-      uint32_t v = __ldg(in + (size_t)(base + t) * count + idx);
-      a0 += (uint64_t)v * p.x; a1 += (uint64_t)v * p.y; a2 += (uint64_t)v * p.z; a3 += (uint64_t)v * p.w;
-      any = true;
-      if (++terms == 2) { a0 = fixhi(a0); a1 = fixhi(a1); a2 = fixhi(a2); a3 = fixhi(a3); terms = 0; }
+    if (threadIdx.x < 32) {
+      uint32_t cnt = 0;
+      for (uint32_t t0 = 0; t0 < chunk; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool hit = t < chunk && s_combo[t] == combo;
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+        cnt += __popc(m);
+      }
+      if (lane == 0) s_hits = cnt;
+    }
+    __syncthreads();
+    const uint32_t hits = s_hits;
+    if (!live || hits == 0) continue;
+    any = true;
+    const uint32_t* col0 = in + (size_t)base * count + idx;
+    for (uint32_t k = 0; k < hits; k += 4) {
+      uint32_t v[4]; uint4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool on = k + u < hits;
+        const uint32_t t = on ? s_list[k + u] : 0u;
+        v[u] = on ? __ldg(col0 + (size_t)t * count) : 0u;        // a zero coefficient adds nothing
+        p[u] = s_pw[t];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u += 2) {
+        a0 += (uint64_t)v[u] * p[u].x; a1 += (uint64_t)v[u] * p[u].y; a2 += (uint64_t)v[u] * p[u].z; a3 += (uint64_t)v[u] * p[u].w;
+        a0 += (uint64_t)v[u + 1] * p[u + 1].x; a1 += (uint64_t)v[u + 1] * p[u + 1].y; a2 += (uint64_t)v[u + 1] * p[u + 1].z; a3 += (uint64_t)v[u + 1] * p[u + 1].w;
+        a0 = fixhi(a0); a1 = fixhi(a1); a2 = fixhi(a2); a3 = fixhi(a3);
+      }
     }
   }
   if (live && any) {
@@ -174,6 +200,69 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict_
   }
 }
 
+// Four consecutive coefficients per thread (one 128-bit load per column, 512 contiguous bytes per warp and column): with one word per
+// thread every warp request was a lone 128-byte line 4 MB away from the previous one, and the sweep ran at the random-access rate of
+// the HBM (1.9 TB/s): 0.51 -> 0.27 ms for 224 x 2^20 on B200.  Used when count is a multiple of 4 (every power-of-two size above 2).
+__global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs4(uint4* __restrict__ out, const uint4* __restrict__ pw, const uint32_t* __restrict__ in,
+                                                                const uint32_t* __restrict__ combos, uint32_t input_size, size_t count) {
+  __shared__ uint4 s_pw[MIX_CHUNK];
+  __shared__ uint32_t s_combo[MIX_CHUNK];
+  __shared__ uint16_t s_list[MIX_CHUNK + 2];
+  __shared__ uint32_t s_hits;
+  const uint32_t combo = blockIdx.y, lane = threadIdx.x & 31;
+  const size_t idx = ((size_t)blockIdx.x * EW_BLOCK + threadIdx.x) * 4;
+  const bool live = idx < count;
+  uint64_t a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0; }
+  bool any = false;
+  for (uint32_t base = 0; base < input_size; base += MIX_CHUNK) {
+    uint32_t chunk = min((uint32_t)MIX_CHUNK, input_size - base);
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < chunk; t += EW_BLOCK) { s_pw[t] = pw[base + t]; s_combo[t] = combos[base + t]; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t cnt = 0;
+      for (uint32_t t0 = 0; t0 < chunk; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool hit = t < chunk && s_combo[t] == combo;
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+        cnt += __popc(m);
+      }
+      if (lane == 0) s_hits = cnt;
+    }
+    __syncthreads();
+    const uint32_t hits = s_hits;
+    if (!live || hits == 0) continue;
+    any = true;
+    const uint32_t* col0 = in + (size_t)base * count + idx;
+    for (uint32_t k = 0; k < hits; k += 2) {
+      const bool on1 = k + 1 < hits;
+      const uint32_t t0 = s_list[k], t1 = on1 ? s_list[k + 1] : 0u;
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(col0 + (size_t)t0 * count));
+      const uint4 v1 = on1 ? __ldg(reinterpret_cast<const uint4*>(col0 + (size_t)t1 * count)) : make_uint4(0u, 0u, 0u, 0u);      // a zero coefficient adds nothing
+      const uint4 p0 = s_pw[t0], p1 = s_pw[t1];
+      const uint32_t c0[4] = {v0.x, v0.y, v0.z, v0.w}, c1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a[r][0] += (uint64_t)c0[r] * p0.x; a[r][1] += (uint64_t)c0[r] * p0.y; a[r][2] += (uint64_t)c0[r] * p0.z; a[r][3] += (uint64_t)c0[r] * p0.w;
+        a[r][0] += (uint64_t)c1[r] * p1.x; a[r][1] += (uint64_t)c1[r] * p1.y; a[r][2] += (uint64_t)c1[r] * p1.z; a[r][3] += (uint64_t)c1[r] * p1.w;
+        a[r][0] = fixhi(a[r][0]); a[r][1] = fixhi(a[r][1]); a[r][2] = fixhi(a[r][2]); a[r][3] = fixhi(a[r][3]);
+      }
+    }
+  }
+  if (live && any) {
+    uint4* o = out + (size_t)combo * count + idx;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint4 cur = o[r];
+      Fp4 v = ld4(cur) + Fp4::raw(fin_acc(a[r][0]), fin_acc(a[r][1]), fin_acc(a[r][2]), fin_acc(a[r][3]));
+      o[r] = st4(v);
+    }
+  }
+}
+
 // ---- batch_evaluate_any (DEEP) -------------------------------------------------------------------------
 // out[j] = sum_i coeffs[which[j]][i] * x_j^i with Fp coefficients and an Fp4 point.  Write i = slab * SLAB + m * 256 + t
 // (t = thread, m = step): thread t of block (slab, j) accumulates sum_m c[..] * (x^256)^m LAZILY -- one IMAD.WIDE per
@@ -181,34 +270,38 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs(uint4* __restrict_
 // (see fixhi) -- and only then multiplies by x^t, reduces over the block and scales by x^(slab * SLAB).  All powers come
 // from per-point tables built by a small pre-kernel, so the main loop is 4 IMAD.WIDE + 2 fix-ups per coefficient
 // (the canonical form costs 4 Montgomery multiplications + 4 modular additions).
-constexpr int EVAL_THREADS = 256, EVAL_WARPS = EVAL_THREADS / 32, EVAL_STEPS = 64;
-constexpr size_t EVAL_SLAB = (size_t)EVAL_THREADS * EVAL_STEPS;     // 16384 coefficients
-// tables per evaluation point j: [x^t, t < 256][x^(256 m), m < 64][x^(slab * SLAB), slab < n_slabs]
-__host__ __device__ inline size_t eval_table_stride(uint32_t n_slabs) { return (size_t)EVAL_THREADS + EVAL_STEPS + n_slabs; }
-__global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restrict__ xs, uint32_t n_slabs, uint32_t n_eval) {
-  const size_t stride = eval_table_stride(n_slabs);
+// STEPS coefficients per thread: the block epilogue (an Fp4 product by x^t, the block reduction, an Fp4 product by x^(slab base)) costs as
+// much multiplier-pipe time as ~45 coefficients, so large launches use 256 steps per thread (0.60 -> 0.535 ms for 448 points x 2^20 on B200),
+// small ones 64 (more blocks, less predicated-off work).
+constexpr int EVAL_THREADS = 256, EVAL_WARPS = EVAL_THREADS / 32;
+// tables per evaluation point j: [x^t, t < 256][x^(256 m), m < steps][x^(slab * slab_size), slab < n_slabs]
+__host__ __device__ inline size_t eval_table_stride(uint32_t steps, uint32_t n_slabs) { return (size_t)EVAL_THREADS + steps + n_slabs; }
+__global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restrict__ xs, uint32_t steps, uint32_t n_slabs, uint32_t n_eval) {
+  const size_t stride = eval_table_stride(steps, n_slabs);
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= stride * n_eval) return;
   uint32_t j = (uint32_t)(g / stride), e = (uint32_t)(g % stride);
   uint4 xv = xs[j];
-  uint64_t exp = e < EVAL_THREADS ? e : e < EVAL_THREADS + EVAL_STEPS ? (uint64_t)(e - EVAL_THREADS) * EVAL_THREADS : (uint64_t)(e - EVAL_THREADS - EVAL_STEPS) * EVAL_SLAB;
+  uint64_t exp = e < EVAL_THREADS ? e : e < EVAL_THREADS + steps ? (uint64_t)(e - EVAL_THREADS) * EVAL_THREADS : (uint64_t)(e - EVAL_THREADS - steps) * EVAL_THREADS * steps;
   Fp4 r = pow(ld4(xv), exp);
   tables[g] = st4(r);
 }
+template <int STEPS>
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__ partial, const uint32_t* __restrict__ coeffs, size_t n,
                                                               const uint32_t* __restrict__ which, const uint4* __restrict__ tables, uint32_t n_slabs) {
-  __shared__ uint4 s_pw[EVAL_STEPS];
+  __shared__ uint4 s_pw[STEPS];
   __shared__ uint4 s_red[EVAL_WARPS];
+  constexpr size_t SLAB = (size_t)EVAL_THREADS * STEPS;
   const uint32_t slab = blockIdx.x, j = blockIdx.y;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint4* tab = tables + (size_t)j * eval_table_stride(n_slabs);
-  if (threadIdx.x < EVAL_STEPS) s_pw[threadIdx.x] = tab[EVAL_THREADS + threadIdx.x];
+  const uint4* tab = tables + (size_t)j * eval_table_stride(STEPS, n_slabs);
+  for (int i = threadIdx.x; i < STEPS; i += EVAL_THREADS) s_pw[i] = tab[EVAL_THREADS + i];
   __syncthreads();
   const uint32_t* col = coeffs + (size_t)which[j] * n;
-  const size_t base = (size_t)slab * EVAL_SLAB + threadIdx.x;
+  const size_t base = (size_t)slab * SLAB + threadIdx.x;
   uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll 8
-  for (int m = 0; m < EVAL_STEPS; m += 2) {
+  for (int m = 0; m < STEPS; m += 2) {
     size_t i0 = base + (size_t)m * EVAL_THREADS, i1 = i0 + EVAL_THREADS;
     uint32_t c0 = i0 < n ? __ldg(col + i0) : 0u, c1 = i1 < n ? __ldg(col + i1) : 0u;
     uint4 p0 = s_pw[m], p1 = s_pw[m + 1];
@@ -230,7 +323,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__
   if (threadIdx.x == 0) {
     Fp4 t;
     for (int w = 0; w < EVAL_WARPS; ++w) { uint4 v = s_red[w]; t += ld4(v); }
-    uint4 xs = tab[EVAL_THREADS + EVAL_STEPS + slab];
+    uint4 xs = tab[EVAL_THREADS + STEPS + slab];
     t *= ld4(xs);
     partial[(size_t)j * n_slabs + slab] = st4(t);
   }
@@ -391,21 +484,33 @@ void mix_poly_coeffs(zkb_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp
   if (!input_size || !count) return;
   uint4* pw = (uint4*)scratch(ctx, input_size * 16);
   k_mix_powers<<<grid_for(input_size, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(pw, to_arg(mix_start), to_arg(mix), (uint32_t)input_size); launched(ctx);
-  dim3 grid(grid_for(count, EW_BLOCK), n_combo_slots);
-  k_mix_poly_coeffs<<<grid, EW_BLOCK, 0, ctx->stream>>>((uint4*)out, pw, in, d_combos, (uint32_t)input_size, count); launched(ctx);
+  if (count % 4 == 0 && ((uintptr_t)in & 15) == 0) {
+    dim3 grid(grid_for(count / 4, EW_BLOCK), n_combo_slots);
+    k_mix_poly_coeffs4<<<grid, EW_BLOCK, 0, ctx->stream>>>((uint4*)out, pw, in, d_combos, (uint32_t)input_size, count);
+  } else {
+    dim3 grid(grid_for(count, EW_BLOCK), n_combo_slots);
+    k_mix_poly_coeffs<<<grid, EW_BLOCK, 0, ctx->stream>>>((uint4*)out, pw, in, d_combos, (uint32_t)input_size, count);
+  }
+  launched(ctx);
 }
 void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval) {
   if (!n_eval) return;
   size_t n = (size_t)1 << po2;
-  uint32_t n_slabs = (uint32_t)((n + EVAL_SLAB - 1) / EVAL_SLAB);
-  const size_t stride = eval_table_stride(n_slabs);
+  static int forced = [] { const char* e = getenv("ZKB_EVAL_STEPS"); return e ? atoi(e) : 0; }();
+  // 256 steps only when that still leaves several blocks per SM (16 evaluation points of a 2^20 column: 256 blocks -- too few)
+  const uint32_t steps = forced == 64 || forced == 256 ? (uint32_t)forced : (po2 >= 18 && n_eval * (n >> 16) >= 1024 ? 256u : 64u);
+  const size_t slab = (size_t)EVAL_THREADS * steps;
+  uint32_t n_slabs = (uint32_t)((n + slab - 1) / slab);
+  const size_t stride = eval_table_stride(steps, n_slabs);
   uint4* partial = (uint4*)scratch(ctx, (n_eval * n_slabs + n_eval * stride) * 16);
   uint4* tables = partial + n_eval * n_slabs;
-  k_eval_tables<<<grid_for(stride * n_eval, 128), 128, 0, ctx->stream>>>(tables, (const uint4*)d_xs, n_slabs, (uint32_t)n_eval); launched(ctx);
+  k_eval_tables<<<grid_for(stride * n_eval, 128), 128, 0, ctx->stream>>>(tables, (const uint4*)d_xs, steps, n_slabs, (uint32_t)n_eval); launched(ctx);
   for (size_t j0 = 0; j0 < n_eval; j0 += 32768) {      // grid.y limit
     uint32_t nj = (uint32_t)std::min<size_t>(32768, n_eval - j0);
     dim3 grid(n_slabs, nj);
-    k_eval_slabs<<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs); launched(ctx);
+    if (steps == 256) k_eval_slabs<256><<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs);
+    else k_eval_slabs<64><<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs);
+    launched(ctx);
   }
   k_eval_reduce<<<grid_for(n_eval, 128), 128, 0, ctx->stream>>>((uint4*)d_out, partial, n_slabs, (uint32_t)n_eval); launched(ctx);
 }
