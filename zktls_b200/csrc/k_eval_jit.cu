@@ -207,14 +207,17 @@ static Analysis analyse(const CircuitDef& c) {
   return A;
 }
 
-// Shared-memory staged form (mode "staged"): a CTA owns SG_BLOCK consecutive domain points.  The columns its constraints
+// Shared-memory staged form (mode "staged"): a CTA owns SG_BLOCK (512) consecutive domain points.  The columns its constraints
 // read are brought into shared memory by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) issued by one
 // elected thread: columns read many times (the code group's constants) stay resident, the others stream through a ring of
 // `stages` slots of `cps` columns, refilled `stages` blocks ahead of their use.  Taps then are LDS with an immediate offset
 // (row - 4 back is the same column slot, a few words earlier: the slot holds `halo` rows in front of the tile), the loads
 // in flight per SM are decoupled from the register file (ring bytes instead of registers), and no address arithmetic runs
 // on the multiplier pipe.
-constexpr int SG_BLOCK = 256;
+// threads (= domain points) per staged CTA; ZKB_EC_BLOCK in {128, 256, 512, 1024}.  Measured (SYN-280, 2^22 points): 128: 2.25 ms, 256: 1.79 ms,
+// 512: 1.60 ms, 1024: 1.70 ms -- longer contiguous copies per column (2 KB) use the HBM better, at the same 2048 threads per SM.
+static int sg_block() { const char* e = getenv("ZKB_EC_BLOCK"); int v = e ? atoi(e) : 512; return v == 128 || v == 256 || v == 1024 ? v : 512; }
+#define SG_BLOCK sg_block()
 struct GenInfo {
   uint32_t n_powers = 1;
   int block = JIT_BLOCK;     // threads per CTA
@@ -267,8 +270,9 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
       halo = std::max(halo, 4 * t.back);
     }
     const uint32_t res_max = env_u32("ZKB_EC_RES", 32, 0, 64), res_min_uses = env_u32("ZKB_EC_RES_USES", 4, 2, 1u << 30);
-    // measured on B200, SYN-280 (profiles/r1_o_ec_staged.txt): 2 stages x 6 columns = 1.82 ms (28 KB per CTA: eight CTAs = 2048 threads per
-    // SM), 3 x 6: 1.89-1.96 ms; deeper or wider rings cost occupancy (6 x 8: 3.25 ms, 10 x 8: 4.35 ms); the register form takes 2.4-2.5 ms
+    // measured on B200, SYN-280 (profiles/r1_o_ec_staged.txt), 256-point CTAs: 2 stages x 6 columns = 1.82 ms (28 KB per CTA: eight CTAs = 2048
+    // threads per SM), 3 x 6: 1.89-1.96 ms; deeper or wider rings cost occupancy (6 x 8: 3.25 ms, 10 x 8: 4.35 ms); the register form takes
+    // 2.4-2.5 ms.  With 512-point CTAs (the default): 2 x 6 = 1.60 ms, 2 x 4 = 1.65 ms, 2 x 8 = 1.86 ms, 3 x 6 = 1.99 ms.
     cps = env_u32("ZKB_EC_CPS", 6, 1, 32); stages = env_u32("ZKB_EC_STAGES", 2, 2, 16);
     std::vector<ColUse> cand;
     for (auto& kv : uses) if (kv.second >= res_min_uses) cand.push_back({kv.first.first, kv.first.second, kv.second});
@@ -307,7 +311,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
   } else {
     o << "#define PW(k) __ldg(pw + (k))\n#define GL(i) __ldg(gl + (i))\n";
   }
-  const int ctas_per_sm = staged ? (int)std::max<size_t>(1, std::min<size_t>(env_u32("ZKB_EC_MINBLOCKS", 8, 1, 16), (220 * 1024) / (gi.smem + 1024))) : min_blocks();
+  const int ctas_per_sm = staged ? (int)std::max<size_t>(1, std::min<size_t>(env_u32("ZKB_EC_MINBLOCKS", 8, 1, 16), (227 * 1024) / (gi.smem + 1024))) : min_blocks();
   o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", " << ctas_per_sm << ") zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
        << (staged ? "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));     // opaque: see the note on uniform address arithmetic below\n"
