@@ -8,10 +8,14 @@ a = ap.parse_args()
 hal = B200Hal(0); n = 1 << a.po2
 if a.op == "hash_rows":
     rows = 4 * n; m = hal.alloc_elem(rows * a.cols); d = hal.alloc_digest(rows)
+    hal.hash_rows(d, m); hal.sync(); hal.timer_start()
     for _ in range(a.reps): hal.hash_rows(d, m)
+    print(f"hash_rows {a.cols} x 2^{a.po2 + 2}: {hal.timer_stop() / a.reps:.3f} ms")
 elif a.op == "merkle":
     rows = 4 * n; d = hal.alloc_digest(2 * rows)
+    hal.merkle_build(d, rows); hal.sync(); hal.timer_start()
     for _ in range(a.reps): hal.merkle_build(d, rows)
+    print(f"merkle_build 2^{a.po2 + 2} leaves: {hal.timer_stop() / a.reps:.3f} ms  env", {k: v for k, v in os.environ.items() if k.startswith("ZKB_")})
 elif a.op == "intt":
     b = hal.alloc_elem(a.cols * n)
     hal.batch_interpolate_ntt_zk_shift(b, a.cols); hal.sync(); hal.timer_start()
