@@ -72,15 +72,15 @@ __global__ void k_bit_reverse(uint32_t* __restrict__ io, int po2, size_t count) 
 // rev(i) = (rev(b), rev(m), rev(a)), so the 2^T x 2^T tile (a, b) of slice m lands, transposed and with both tile
 // coordinates bit-reversed, in slice rev(m).  One CTA owns the pair of slices {m, rev(m)}: every global access is a row
 // of 2^T consecutive words (128 / 256 bytes) and the permutation itself happens in shared memory.
-template <int T>
-__global__ void __launch_bounds__(256) k_bit_reverse_tiled(uint32_t* __restrict__ io, int po2) {
+template <int T, typename E = uint32_t>
+__global__ void __launch_bounds__(256) k_bit_reverse_tiled(E* __restrict__ io, int po2) {
   constexpr int W = 1 << T;
-  __shared__ uint32_t A[W][W + 1], B[W][W + 1];
+  __shared__ E A[W][W + 1], B[W][W + 1];
   const int mid_bits = po2 - 2 * T;
   const uint32_t m = blockIdx.x & ((1u << mid_bits) - 1u);
   const uint32_t rm = bit_rev32(m, mid_bits);
   if (m > rm) return;
-  uint32_t* base = io + ((size_t)(blockIdx.x >> mid_bits) << po2);
+  E* base = io + ((size_t)(blockIdx.x >> mid_bits) << po2);
   const int hi_shift = po2 - T;
   const bool pair = m != rm;
   for (uint32_t e = threadIdx.x; e < W * W; e += 256) {
@@ -94,6 +94,19 @@ __global__ void __launch_bounds__(256) k_bit_reverse_tiled(uint32_t* __restrict_
     uint32_t ra = bit_rev32(a, T), rb = bit_rev32(b, T);
     base[((size_t)a << hi_shift) | (rm << T) | b] = A[rb][ra];
     if (pair) base[((size_t)a << hi_shift) | (m << T) | b] = B[rb][ra];
+  }
+}
+// the same permutation over arrays of 16-byte elements (Fp4 coefficients), small sizes
+__global__ void k_bit_reverse_ext(uint4* __restrict__ io, int po2, size_t count) {
+  size_t n = (size_t)1 << po2;
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * count) return;
+  uint32_t i = (uint32_t)(g & (n - 1));
+  uint32_t r = bit_rev32(i, po2);
+  if (i < r) {
+    uint4* col = io + (g - i);
+    uint4 a = col[i], b = col[r];
+    col[i] = b; col[r] = a;
   }
 }
 // io[c][i] *= 3^bitrev(i)
@@ -276,13 +289,17 @@ __global__ void __launch_bounds__(EW_BLOCK) k_mix_poly_coeffs4(uint4* __restrict
 constexpr int EVAL_THREADS = 256, EVAL_WARPS = EVAL_THREADS / 32;
 // tables per evaluation point j: [x^t, t < 256][x^(256 m), m < steps][x^(slab * slab_size), slab < n_slabs]
 __host__ __device__ inline size_t eval_table_stride(uint32_t steps, uint32_t n_slabs) { return (size_t)EVAL_THREADS + steps + n_slabs; }
-__global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restrict__ xs, uint32_t steps, uint32_t n_slabs, uint32_t n_eval) {
+// brev_po2 > 0: the coefficient array is in BIT-REVERSED order (position p holds the coefficient of x^rev(p), rev over brev_po2 bits).
+// A position splits into disjoint bit fields p = t + 256 m + 256 steps slab, and rev(p) is the sum of the reversed fields, so the
+// same three tables work with the exponents rev(t), rev(256 m), rev(256 steps slab) -- no data movement.
+__global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restrict__ xs, uint32_t steps, uint32_t n_slabs, uint32_t n_eval, int brev_po2) {
   const size_t stride = eval_table_stride(steps, n_slabs);
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= stride * n_eval) return;
   uint32_t j = (uint32_t)(g / stride), e = (uint32_t)(g % stride);
   uint4 xv = xs[j];
   uint64_t exp = e < EVAL_THREADS ? e : e < EVAL_THREADS + steps ? (uint64_t)(e - EVAL_THREADS) * EVAL_THREADS : (uint64_t)(e - EVAL_THREADS - steps) * EVAL_THREADS * steps;
+  if (brev_po2 > 0) exp = (exp >> brev_po2) ? 0 : bit_rev32((uint32_t)exp, brev_po2);      // positions >= n are never read
   Fp4 r = pow(ld4(xv), exp);
   tables[g] = st4(r);
 }
@@ -466,6 +483,14 @@ void batch_bit_reverse(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
   }
   k_bit_reverse<<<grid_for(total, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(io, po2, count); launched(ctx);
 }
+// in-place bit reversal of `count` arrays of 2^po2 Fp4 elements
+void batch_bit_reverse_ext(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
+  size_t total = count << po2;
+  if (!total || po2 == 0) return;
+  if (po2 >= 10 && (count << (po2 - 10)) < (1u << 31)) k_bit_reverse_tiled<5, uint4><<<(unsigned)(count << (po2 - 10)), 256, 0, ctx->stream>>>((uint4*)io, po2);
+  else k_bit_reverse_ext<<<grid_for(total, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>((uint4*)io, po2, count);
+  launched(ctx);
+}
 void zk_shift(zkb_ctx* ctx, uint32_t* io, size_t count, int po2) {
   size_t n = (size_t)1 << po2;
   if (!count) return;
@@ -493,7 +518,7 @@ void mix_poly_coeffs(zkb_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp
   }
   launched(ctx);
 }
-void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval) {
+void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval, bool coeffs_bit_reversed) {
   if (!n_eval) return;
   size_t n = (size_t)1 << po2;
   static int forced = [] { const char* e = getenv("ZKB_EVAL_STEPS"); return e ? atoi(e) : 0; }();
@@ -504,7 +529,7 @@ void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uin
   const size_t stride = eval_table_stride(steps, n_slabs);
   uint4* partial = (uint4*)scratch(ctx, (n_eval * n_slabs + n_eval * stride) * 16);
   uint4* tables = partial + n_eval * n_slabs;
-  k_eval_tables<<<grid_for(stride * n_eval, 128), 128, 0, ctx->stream>>>(tables, (const uint4*)d_xs, steps, n_slabs, (uint32_t)n_eval); launched(ctx);
+  k_eval_tables<<<grid_for(stride * n_eval, 128), 128, 0, ctx->stream>>>(tables, (const uint4*)d_xs, steps, n_slabs, (uint32_t)n_eval, coeffs_bit_reversed ? po2 : 0); launched(ctx);
   for (size_t j0 = 0; j0 < n_eval; j0 += 32768) {      // grid.y limit
     uint32_t nj = (uint32_t)std::min<size_t>(32768, n_eval - j0);
     dim3 grid(n_slabs, nj);
@@ -633,7 +658,7 @@ zkb_err zkb_batch_evaluate_any(zkb_ctx* ctx, const void* d_coeffs, size_t poly_c
   ZKB_API_BEGIN use(ctx); check_po2(po2); (void)poly_count;
   ZKB_REQUIRE((d_coeffs && d_which && d_xs && d_out) || !n_eval, "null buffer");
   ZKB_REQUIRE(aligned16(d_xs) && aligned16(d_out), "xs/out must be 16-byte aligned");
-  batch_evaluate_any(ctx, (const uint32_t*)d_coeffs, po2, (const uint32_t*)d_which, (const uint32_t*)d_xs, (uint32_t*)d_out, n_eval);
+  batch_evaluate_any(ctx, (const uint32_t*)d_coeffs, po2, (const uint32_t*)d_which, (const uint32_t*)d_xs, (uint32_t*)d_out, n_eval, false);
   ZKB_API_END
 }
 zkb_err zkb_poly_divide(zkb_ctx* ctx, void* d_poly, size_t n, const uint32_t* h_z, void* d_rem) {

@@ -21,12 +21,15 @@ void fill_u32(zkb_ctx* ctx, uint32_t* x, size_t n, uint32_t v);
 void gather_sample(zkb_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride);
 void batch_expand(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, int in_po2, int expand_bits);
 void batch_bit_reverse(zkb_ctx* ctx, uint32_t* io, size_t count, int po2);
+void batch_bit_reverse_ext(zkb_ctx* ctx, uint32_t* io, size_t count, int po2);      // arrays of Fp4 (16-byte) elements
 void zk_shift(zkb_ctx* ctx, uint32_t* io, size_t count, int po2);
 void eltwise_sum_extelem(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t count, size_t to_add);
 void fri_fold(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, const Fp4& mix, size_t m);
 void mix_poly_coeffs(zkb_ctx* ctx, uint32_t* out, const Fp4& mix_start, const Fp4& mix, const uint32_t* in, const uint32_t* d_combos,
                      size_t input_size, size_t count, uint32_t n_combo_slots);
-void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval);
+// coeffs_bit_reversed: the columns hold their coefficients in bit-reversed order (as the iNTT leaves them); same results
+void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uint32_t* d_which, const uint32_t* d_xs, uint32_t* d_out, size_t n_eval,
+                        bool coeffs_bit_reversed = false);
 void poly_divide(zkb_ctx* ctx, uint32_t* d_poly, size_t n, const Fp4& z, uint32_t* d_rem);
 void prefix_products(zkb_ctx* ctx, uint32_t* d_io, size_t n);
 // k_eval_check.cu

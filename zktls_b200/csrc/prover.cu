@@ -86,13 +86,14 @@ struct PolyGroup {
   size_t count = 0, n = 0;
   DevBuf coeffs, evaluated;
   DeviceMerkle merkle;
-  // takes ownership of bit-reversed coefficients (count x n)
+  // takes ownership of bit-reversed coefficients (count x n).  The reference bit-reverses them here (poly_group.rs) because its DEEP
+  // evaluation and mix read natural order; here `coeffs` STAYS bit-reversed -- batch_evaluate_any takes the order as a flag, the mix is
+  // elementwise, and only the three combo polynomials are put in natural order afterwards (48 MB instead of 1.24 GB per segment).
   void build(zkb_ctx* ctx, DevBuf&& c, size_t count_, int po2) {
     count = count_; n = (size_t)1 << po2;
     coeffs = std::move(c);
     evaluated = DevBuf(ctx, count * n * INV_RATE);
     ntt_forward(ctx, evaluated.p, coeffs.p, count, po2 + 2, 2);
-    batch_bit_reverse(ctx, coeffs.p, count, po2);
     merkle.build(ctx, evaluated.p, n * INV_RATE, count);
   }
 };
@@ -281,9 +282,9 @@ struct zkb_prover {
       h2d(ctx, d_xs.p, all_xs.data(), all_xs.size() * 16);
       for (uint32_t g = 0; g < 3; ++g) {
         size_t b = c.group_tap_begin(g), e = c.group_tap_end(g);
-        batch_evaluate_any(ctx, groups[g].coeffs.p, po2, d_which.p + b, d_xs.p + 4 * b, d_out.p + 4 * b, e - b);
+        batch_evaluate_any(ctx, groups[g].coeffs.p, po2, d_which.p + b, d_xs.p + 4 * b, d_out.p + 4 * b, e - b, true);
       }
-      batch_evaluate_any(ctx, check_group.coeffs.p, po2, d_which.p + tap_size, d_xs.p + 4 * tap_size, d_out.p + 4 * tap_size, CHECK_SIZE);
+      batch_evaluate_any(ctx, check_group.coeffs.p, po2, d_which.p + tap_size, d_xs.p + 4 * tap_size, d_out.p + 4 * tap_size, CHECK_SIZE, true);
       d2h(ctx, eval_u.data(), d_out.p, eval_u.size() * 16);
     }
     pt.mark("finalize: DEEP evaluations");
@@ -314,6 +315,7 @@ struct zkb_prover {
         off += cols;
       }
       mix_poly_coeffs(ctx, combos.p, cur, mix_c, check_group.coeffs.p, d_ids.p + off, CHECK_SIZE, n, (uint32_t)combos_size + 1);
+      batch_bit_reverse_ext(ctx, combos.p, combos_size + 1, po2);      // the mix ran over bit-reversed coefficients: natural order from here on
     }
     pt.mark("finalize: coeff_u + mix_poly_coeffs");
     // 6. subtract the interpolants (touches only the lowest coefficients), then divide on the device
