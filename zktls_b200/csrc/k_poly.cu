@@ -303,27 +303,39 @@ __global__ void k_eval_tables(uint4* __restrict__ tables, const uint4* __restric
   Fp4 r = pow(ld4(xv), exp);
   tables[g] = st4(r);
 }
-template <int STEPS>
+// acc + a * b as ONE IMAD.WIDE.  Spelled in PTX because `acc += (uint64_t)c * p` with c = (in range ? load : 0) made the compiler carry c
+// as a 64-bit pair with a zero high word and emit a 64 x 32 bit product: an extra IMAD and add per term on the multiplier pipe the kernel
+// is bound by (ncu: fmaheavy 79 %).
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t acc) {
+  uint64_t d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(acc));
+  return d;
+}
+// FULL: n is a multiple of the slab (every power-of-two n >= 256 * STEPS): no bounds checks in the loop
+template <int STEPS, bool FULL>
 __global__ void __launch_bounds__(EVAL_THREADS) k_eval_slabs(uint4* __restrict__ partial, const uint32_t* __restrict__ coeffs, size_t n,
                                                               const uint32_t* __restrict__ which, const uint4* __restrict__ tables, uint32_t n_slabs) {
   __shared__ uint4 s_pw[STEPS];
   __shared__ uint4 s_red[EVAL_WARPS];
-  constexpr size_t SLAB = (size_t)EVAL_THREADS * STEPS;
+  constexpr uint32_t SLAB = (uint32_t)EVAL_THREADS * STEPS;
   const uint32_t slab = blockIdx.x, j = blockIdx.y;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint4* tab = tables + (size_t)j * eval_table_stride(STEPS, n_slabs);
   for (int i = threadIdx.x; i < STEPS; i += EVAL_THREADS) s_pw[i] = tab[EVAL_THREADS + i];
   __syncthreads();
-  const uint32_t* col = coeffs + (size_t)which[j] * n;
-  const size_t base = (size_t)slab * SLAB + threadIdx.x;
+  const uint32_t n32 = (uint32_t)n;                        // n <= 2^26
+  const uint32_t base = slab * SLAB + threadIdx.x;
+  const uint32_t* col = coeffs + (size_t)which[j] * n + base;
   uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll 8
   for (int m = 0; m < STEPS; m += 2) {
-    size_t i0 = base + (size_t)m * EVAL_THREADS, i1 = i0 + EVAL_THREADS;
-    uint32_t c0 = i0 < n ? __ldg(col + i0) : 0u, c1 = i1 < n ? __ldg(col + i1) : 0u;
+    const uint32_t o0 = (uint32_t)m * EVAL_THREADS, o1 = o0 + EVAL_THREADS;
+    uint32_t c0, c1;
+    if (FULL) { c0 = __ldg(col + o0); c1 = __ldg(col + o1); }
+    else { c0 = base + o0 < n32 ? __ldg(col + o0) : 0u; c1 = base + o1 < n32 ? __ldg(col + o1) : 0u; }
     uint4 p0 = s_pw[m], p1 = s_pw[m + 1];
-    a0 += (uint64_t)c0 * p0.x; a1 += (uint64_t)c0 * p0.y; a2 += (uint64_t)c0 * p0.z; a3 += (uint64_t)c0 * p0.w;
-    a0 += (uint64_t)c1 * p1.x; a1 += (uint64_t)c1 * p1.y; a2 += (uint64_t)c1 * p1.z; a3 += (uint64_t)c1 * p1.w;
+    a0 = mad_wide(c0, p0.x, a0); a1 = mad_wide(c0, p0.y, a1); a2 = mad_wide(c0, p0.z, a2); a3 = mad_wide(c0, p0.w, a3);
+    a0 = mad_wide(c1, p1.x, a0); a1 = mad_wide(c1, p1.y, a1); a2 = mad_wide(c1, p1.z, a2); a3 = mad_wide(c1, p1.w, a3);
     a0 = fixhi(a0); a1 = fixhi(a1); a2 = fixhi(a2); a3 = fixhi(a3);
   }
   Fp4 acc = Fp4::raw(fin_acc(a0), fin_acc(a1), fin_acc(a2), fin_acc(a3));
@@ -533,8 +545,11 @@ void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uin
   for (size_t j0 = 0; j0 < n_eval; j0 += 32768) {      // grid.y limit
     uint32_t nj = (uint32_t)std::min<size_t>(32768, n_eval - j0);
     dim3 grid(n_slabs, nj);
-    if (steps == 256) k_eval_slabs<256><<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs);
-    else k_eval_slabs<64><<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs);
+    const bool full = n % slab == 0;
+#define ZKB_SLABS(ST, FL) k_eval_slabs<ST, FL><<<grid, EVAL_THREADS, 0, ctx->stream>>>(partial + j0 * n_slabs, coeffs, n, d_which + j0, tables + j0 * stride, n_slabs)
+    if (steps == 256) { if (full) ZKB_SLABS(256, true); else ZKB_SLABS(256, false); }
+    else { if (full) ZKB_SLABS(64, true); else ZKB_SLABS(64, false); }
+#undef ZKB_SLABS
     launched(ctx);
   }
   k_eval_reduce<<<grid_for(n_eval, 128), 128, 0, ctx->stream>>>((uint4*)d_out, partial, n_slabs, (uint32_t)n_eval); launched(ctx);
