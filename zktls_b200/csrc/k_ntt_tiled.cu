@@ -104,6 +104,11 @@ __device__ __forceinline__ uint32_t phys_r(uint32_t pb, int r, int sh) { const u
 // (phys(), whose pad changes every 16 WORDS, made neighbouring rows collide once the tile became 8 wide: 88 M conflict cycles).
 template <int TL> __device__ __forceinline__ uint32_t phys_t(uint32_t x) { return x + ((x >> (4 + TL)) << TL); }
 template <int TL> __device__ __forceinline__ uint32_t phys_tr(uint32_t pb, int r, int sh) { const uint32_t K = (uint32_t)r << sh; return pb + K + ((K >> (4 + TL)) << TL); }
+// the same with the width as an argument (a compile-time constant after unrolling): used by the contiguous pass, whose exchange
+// between the rounds at bits p_prev and pc is conflict-free for BOTH access patterns with TL = min(p_prev, pc) -- with the plain
+// phys() padding the 32 consecutive words a warp touches in the round at bit 8 straddle a pad step (2-way conflicts, 30 M cycles).
+__device__ __forceinline__ uint32_t phys_v(uint32_t x, int tl) { return x + ((x >> (4 + tl)) << tl); }
+__device__ __forceinline__ uint32_t phys_vr(uint32_t pb, int r, int sh, int tl) { const uint32_t K = (uint32_t)r << sh; return pb + K + ((K >> (4 + tl)) << tl); }
 // local index of register r for thread t in a round whose register field starts at bit p
 __device__ __forceinline__ uint32_t local_index(uint32_t t, int p, int r) {
   uint32_t lo = t & ((1u << p) - 1u), hi = t >> p;
@@ -133,12 +138,13 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_inv(uint32_t* __restrict__ 
 #pragma unroll
   for (int p = P0 - 4; p >= 0 || (p > -4 && REM != 0); p -= 4) {
     const int pc = p < 0 ? 0 : p;
-    const uint32_t pb_w = phys(soff + local_index(t, p_prev, 0)), pb_r = phys(soff + local_index(t, pc, 0));
+    const int tl = pc < p_prev ? pc : p_prev;
+    const uint32_t pb_w = phys_v(soff + local_index(t, p_prev, 0), tl), pb_r = phys_v(soff + local_index(t, pc, 0), tl);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[phys_r(pb_w, r, p_prev)] = v[r];
+    for (int r = 0; r < 16; ++r) s[phys_vr(pb_w, r, p_prev, tl)] = v[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
+    for (int r = 0; r < 16; ++r) v[r] = s[phys_vr(pb_r, r, pc, tl)];
     __syncthreads();
     if (p >= 0) radix_round<true, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
     else radix_round<true, 0, (REM == 0 ? 4 : REM)>(v, 0, 0u, twl, ones);
@@ -191,12 +197,13 @@ __global__ void __launch_bounds__(C_THREADS) k_ntt_c_fwd(uint32_t* __restrict__ 
 #pragma unroll
   for (int p = 4; p <= PLAST || (p < PLAST + 4 && REM != 0); p += 4) {
     const int pc = p > PLAST ? PLAST : p;
-    const uint32_t pb_w = phys(soff + local_index(t, p_prev, 0)), pb_r = phys(soff + local_index(t, pc, 0));
+    const int tl = pc < p_prev ? pc : p_prev;
+    const uint32_t pb_w = phys_v(soff + local_index(t, p_prev, 0), tl), pb_r = phys_v(soff + local_index(t, pc, 0), tl);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s[phys_r(pb_w, r, p_prev)] = v[r];
+    for (int r = 0; r < 16; ++r) s[phys_vr(pb_w, r, p_prev, tl)] = v[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = s[phys_r(pb_r, r, pc)];
+    for (int r = 0; r < 16; ++r) v[r] = s[phys_vr(pb_r, r, pc, tl)];
     __syncthreads();
     if (p <= PLAST) radix_round<false, 0, 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
     else radix_round<false, (REM == 0 ? 0 : 4 - REM), 4>(v, pc, t & ((1u << pc) - 1u), twl, ones);
