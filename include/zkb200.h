@@ -167,8 +167,13 @@ zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io);
  * one PCIe link take turns instead of splitting its bandwidth). */
 zkb_err zkb_prover_stage_wait(zkb_prover* p);
 /* CPU verifier for a seal produced by the prover (risc0-zkp verify/*): checks the transcript, Merkle paths, FRI
- * and the constraint relation at the DEEP point.  Host-only, like the reference's verifier. */
-zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words);
+ * and the constraint relation at the DEEP point.  Host-only, like the reference's verifier.
+ * The code group's Merkle root identifies the PROGRAM (risc0: `check_code(po2, root)` against the control ID): it must equal
+ * one of the `n_control_ids` entries of `h_control_ids` (9 words each: po2, code root[8]).  With n_control_ids == 0 the call
+ * is refused unless `h_out_po2_code_root` (9 words, optional otherwise) is given: the caller then receives (po2, code root)
+ * and MUST compare them itself -- a seal whose code trace the prover chose freely proves nothing. */
+zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words,
+                           const uint32_t* h_control_ids, size_t n_control_ids, uint32_t* h_out_po2_code_root);
 
 #ifdef __cplusplus
 }

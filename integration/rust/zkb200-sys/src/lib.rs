@@ -65,7 +65,7 @@ extern "C" {
     pub fn zkb_prover_stage_traces(p: *mut ZkbProver, po2: c_int, h_code: *const c_void, h_data: *const c_void, h_accum: *const c_void) -> ZkbErr;
     pub fn zkb_prove_staged(p: *mut ZkbProver, h_io: *const u32) -> ZkbErr;
     pub fn zkb_prover_stage_wait(p: *mut ZkbProver) -> ZkbErr;
-    pub fn zkb_verify_segment(h_circuit: *const u32, circuit_words: usize, h_seal: *const u32, seal_words: usize) -> ZkbErr;
+    pub fn zkb_verify_segment(h_circuit: *const u32, circuit_words: usize, h_seal: *const u32, seal_words: usize, h_control_ids: *const u32, n_control_ids: usize, h_out_po2_code_root: *mut u32) -> ZkbErr;
 }
 
 /// NULL = Ok; otherwise copy the message, free it with zkb_free_error and return it as an error (risc0-sys `ffi_wrap`).

@@ -243,7 +243,7 @@ static void segment_begin(Prover& p, int po2, const Fp* io, std::vector<Fp>&& co
   p.iop.commit(hash_protocol_info((const uint8_t*)PROOF_SYSTEM_INFO));
   p.iop.commit(hash_protocol_info(c.info));
   std::vector<Fp> hdr(io, io + c.out_size);
-  hdr.push_back(Fp::from((uint32_t)po2));
+  hdr.push_back(Fp::raw((uint32_t)po2));      // Elem::from_u32_slice(&[po2]): a raw reinterpretation, NOT the Montgomery encoding of po2
   p.iop.commit(hash_elem_slice(hdr.data(), hdr.size()));
   p.iop.write_fp(hdr.data(), hdr.size());
   p.set_po2(po2);

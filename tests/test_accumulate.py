@@ -51,7 +51,7 @@ def test_accumulate_is_rejected_for_a_circuit_without_a_witness_program(hal):
 @pytest.mark.parametrize("shape,po2", [(SMALL, 9), (MID, 12)])
 def test_segment_proof_with_device_side_accumulate(hal, oracle, shape, po2):
     """begin() -> accumulate on the device -> finish(device buffer): the seal equals the oracle's (host accum) and verifies."""
-    from zktls_b200.prover import SegmentProver, verify_segment
+    from zktls_b200.prover import SegmentProver, verify_segment, control_id
     blob = circuit.syn_circuit(**shape).blob()
     io, code, data = synth.trace_b_code_data(shape, po2, seed=21)
     code_m, data_m = synth.to_mont(code), synth.to_mont(data)
@@ -66,5 +66,5 @@ def test_segment_proof_with_device_side_accumulate(hal, oracle, shape, po2):
     assert np.array_equal(op.begin(po2, io, code_m, data_m), mix)
     seal_o = op.finish(synth.to_mont(synth.trace_b_accum(shape, po2, 21, code, data, io, mix)))
     assert np.array_equal(seal, seal_o)
-    verify_segment(blob, seal)
+    verify_segment(blob, seal, control_id(po2, op.roots()[0]))
     gp.close()

@@ -44,7 +44,7 @@ def test_staged_source_is_a_bulk_copy_pipeline_and_compiles(shape, cache_dir, mo
         if "libnvrtc" in str(e):
             pytest.skip("libnvrtc not available")
         raise
-    assert [f for f in os.listdir(cache_dir) if f.endswith(".cubin")], "no cubin written"
+    assert [f for f in os.listdir(cache_dir) if f.endswith(".zkbj")], "no cubin written"
 
 
 def test_register_form_still_generated_on_request(cache_dir, monkeypatch):

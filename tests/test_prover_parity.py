@@ -118,7 +118,7 @@ def test_full_size_segment_verifies(hal):
     """BASELINE.json configs[1] at FULL size (2^20 cycles, SYN-280): a witness that satisfies the constraints is proven on the
     GPU and the seal must VERIFY (zkb_verify_segment: Merkle paths, constraint relation at the DEEP point, FRI) -- the
     size-independent property that stands in for an oracle seal the CPU would need minutes to produce."""
-    from zktls_b200.prover import SegmentProver, verify_segment
+    from zktls_b200.prover import SegmentProver, verify_segment, control_id
     from zktls_b200 import ZkbError
     shape, po2 = circuit.SYN280, 20
     blob = circuit.syn_circuit(**shape).blob()
@@ -129,15 +129,16 @@ def test_full_size_segment_verifies(hal):
     accum_m = synth.to_mont(synth.trace_b_accum(shape, po2, 2020, code, data, io, mix))
     seal = gp.finish(accum_m)
     assert gp.roots().shape == (7, 8)
-    verify_segment(blob, seal)
+    cid = control_id(po2, gp.roots()[0])
+    verify_segment(blob, seal, cid)
     bad = seal.copy(); bad[seal.size - 1000] ^= 1
     with pytest.raises(ZkbError):
-        verify_segment(blob, bad)
+        verify_segment(blob, bad, cid)
     # breaking one constraint row makes the proof fail at the DEEP check (the prover itself cannot know)
     data_bad = data_m.copy(); data_bad[12345] = (int(data_bad[12345]) + 1) % 2013265921
     gp.begin(po2, io, code_m, data_bad)
     with pytest.raises(ZkbError):
-        verify_segment(blob, gp.finish(accum_m))
+        verify_segment(blob, gp.finish(accum_m), cid)
     gp.close()
 
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from zktls_b200 import circuit, synth, ZkbError
-from zktls_b200.prover import verify_segment
+from zktls_b200.prover import verify_segment, control_id, seal_code_root
 
 SMALL = dict(accum_cols=4, code_cols=3, data_cols=6, mix_size=5, out_size=4)
 MID = dict(accum_cols=7, code_cols=5, data_cols=33, mix_size=20, out_size=32)
@@ -23,24 +23,26 @@ def oracle_seal(oracle, shape, po2, seed, valid=True):
     else:
         io, code_m, data_m, accum_m = synth.trace_a(shape, po2, seed)
         pr.begin(po2, io, code_m, data_m)
-    return blob, pr.finish(accum_m)
+    seal = pr.finish(accum_m)
+    return blob, seal, control_id(po2, pr.roots()[0])
 
 
 @pytest.mark.parametrize("shape,po2", [(SMALL, 8), (SMALL, 9), (MID, 10), (SMALL, 13)])
 def test_valid_oracle_seal_verifies(oracle, shape, po2):
-    blob, seal = oracle_seal(oracle, shape, po2, seed=3 + po2)
-    verify_segment(blob, seal)
+    blob, seal, cid = oracle_seal(oracle, shape, po2, seed=3 + po2)
+    got_po2, got_root = verify_segment(blob, seal, cid)
+    assert got_po2 == po2 and np.array_equal(got_root, cid[1:])
 
 
 def test_unsatisfied_constraints_are_rejected(oracle):
-    blob, seal = oracle_seal(oracle, SMALL, 8, seed=4, valid=False)
+    blob, seal, cid = oracle_seal(oracle, SMALL, 8, seed=4, valid=False)
     with pytest.raises(ZkbError, match="constraint polynomial"):
-        verify_segment(blob, seal)
+        verify_segment(blob, seal, cid)
 
 
 def test_every_region_of_the_seal_is_bound(oracle):
-    blob, seal = oracle_seal(oracle, SMALL, 8, seed=5)
-    verify_segment(blob, seal)
+    blob, seal, cid = oracle_seal(oracle, SMALL, 8, seed=5)
+    verify_segment(blob, seal, cid)
     rng = np.random.default_rng(1)
     # flip one word at positions spread over the whole seal: header, top layers, coeff_u, FRI commitments, final
     # coefficients and query answers -- every single-word change must be caught
@@ -49,24 +51,57 @@ def test_every_region_of_the_seal_is_bound(oracle):
         bad = seal.copy()
         bad[pos] = (int(bad[pos]) + 1) % 2013265921
         with pytest.raises(ZkbError, match="invalid proof|out of range"):
-            verify_segment(blob, bad)
+            verify_segment(blob, bad, cid)
     with pytest.raises(ZkbError, match="too short"):
-        verify_segment(blob, seal[:-1])
+        verify_segment(blob, seal[:-1], cid)
     with pytest.raises(ZkbError, match="trailing"):
-        verify_segment(blob, np.concatenate([seal, np.zeros(1, np.uint32)]))
+        verify_segment(blob, np.concatenate([seal, np.zeros(1, np.uint32)]), cid)
     # a seal for one circuit does not verify under another circuit's description
     other = circuit.syn_circuit(**dict(SMALL, data_cols=7)).blob()
     with pytest.raises(ZkbError):
-        verify_segment(other, seal)
+        verify_segment(other, seal, cid)
 
 
 def test_golden_seal_verifies():
     import os
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
     blob = circuit.syn_circuit(**SMALL).blob()
-    verify_segment(blob, G["seg_valid_seal"])
+    cid = control_id(int(G["seg_valid_po2"][0]), G["seg_valid_roots"][:8])       # roots in commit order: code first
+    verify_segment(blob, G["seg_valid_seal"], cid)
     with pytest.raises(ZkbError):
-        verify_segment(blob, G["seg_random_seal"])
+        verify_segment(blob, G["seg_random_seal"], control_id(int(G["seg_random_po2"][0]), G["seg_random_roots"][:8]))
+
+
+def test_code_root_is_bound_to_the_control_id(oracle):
+    """the code group is the PROGRAM.  A prover that picks its own code trace -- here an all-zero selector column,
+    which makes every SYN constraint vanish -- can produce an internally consistent seal for ANY io; it must not verify against
+    the genuine program's control ID, and a verifier call that neither checks nor returns the code root is refused."""
+    shape, po2, seed = SMALL, 8, 6
+    blob, seal, cid = oracle_seal(oracle, shape, po2, seed)
+    # the forgery: sel = 0 everywhere, arbitrary data / accum / io
+    io, code, data = synth.trace_b_code_data(shape, po2, seed)
+    code[0][:] = 0
+    forged_io = synth.encode(np.arange(7, 7 + shape["out_size"], dtype=np.uint64)).astype(np.uint32)
+    pr = oracle.Prover(blob)
+    pr.begin(po2, forged_io, synth.to_mont(code), synth.to_mont(data))
+    _, _, _, junk = synth.trace_a(shape, po2, 99)
+    forged = pr.finish(junk)
+    forged_cid = control_id(po2, pr.roots()[0])
+    assert not np.array_equal(forged_cid, cid)
+    verify_segment(blob, forged, forged_cid)                 # consistent with ITS OWN code root: the constraints do vanish ...
+    with pytest.raises(ZkbError, match="control ID"):
+        verify_segment(blob, forged, cid)                    # ... but it is not the program the verifier asked about
+    with pytest.raises(ZkbError, match="control ID"):
+        verify_segment(blob, seal, control_id(po2 + 1, cid[1:]))     # right root, wrong po2
+    verify_segment(blob, seal, np.concatenate([forged_cid, control_id(po2 + 1, cid[1:]), cid]))   # table with several entries
+    assert seal_code_root(blob, seal)[0] == po2 and np.array_equal(seal_code_root(blob, seal)[1], cid[1:])
+    # the C entry point refuses to run with neither a table nor an output buffer
+    import ctypes as C
+    from zktls_b200._lib import lib, check
+    from zktls_b200.hal import _hp, _sz
+    b = np.ascontiguousarray(blob, np.uint32); s_ = np.ascontiguousarray(seal, np.uint32)
+    with pytest.raises(ZkbError, match="control IDs"):
+        check(lib().zkb_verify_segment(_hp(b), _sz(b.size), _hp(s_), _sz(s_.size), None, _sz(0), None))
 
 
 @pytest.mark.gpu
@@ -81,8 +116,9 @@ def test_gpu_seal_verifies(shape, po2):
     code_m, data_m = synth.to_mont(code), synth.to_mont(data)
     mix = gp.begin(po2, io, code_m, data_m)
     seal = gp.finish(synth.to_mont(synth.trace_b_accum(shape, po2, 77, code, data, io, mix)))
-    verify_segment(blob, seal)
+    cid = control_id(po2, gp.roots()[0])
+    verify_segment(blob, seal, cid)
     bad = seal.copy(); bad[seal.size // 2] ^= 1
     with pytest.raises(ZkbError):
-        verify_segment(blob, bad)
+        verify_segment(blob, bad, cid)
     gp.close(); hal.close()

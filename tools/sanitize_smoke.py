@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from zktls_b200 import circuit, synth
 from zktls_b200.hal import B200Hal
-from zktls_b200.prover import SegmentProver, verify_segment
+from zktls_b200.prover import SegmentProver, verify_segment, control_id
 P = 2013265921
 rng = np.random.default_rng(1)
 fp = lambda n: rng.integers(0, P, size=n, dtype=np.uint32)
@@ -26,7 +26,7 @@ io, code, data = synth.trace_b_code_data(shape, po2, 3)
 code_m, data_m = synth.to_mont(code), synth.to_mont(data)
 mix = pr.begin(po2, io, code_m, data_m)
 accum_m = synth.to_mont(synth.trace_b_accum(shape, po2, 3, code, data, io, mix))
-seal = pr.finish(accum_m); verify_segment(blob, seal)
+seal = pr.finish(accum_m); verify_segment(blob, seal, control_id(po2, pr.roots()[0]))
 tr = synth.trace_a(shape, po2, 5)
 pr.stage(po2, *tr[1:]); pr.stage(po2, *tr[1:]); s1 = pr.prove_staged(tr[0]); s2 = pr.prove_staged(tr[0])
 assert np.array_equal(s1, s2)

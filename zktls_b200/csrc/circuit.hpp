@@ -21,6 +21,7 @@ constexpr size_t CIRCUIT_HEADER_WORDS = 16;
 constexpr int GROUP_ACCUM = 0, GROUP_CODE = 1, GROUP_DATA = 2, NUM_GROUPS = 3;
 
 struct TapDef { uint32_t group, column, back; };
+constexpr uint32_t MAX_TAP_BACK = 1u << 12;
 struct RegisterDef { uint32_t group, column, tap_pos, size, combo_id; };
 struct StepDef { uint32_t op, a, b, c; };
 
@@ -56,6 +57,7 @@ struct CircuitDef {
     for (size_t i = 0; i < n_taps; ++i, p += 3) {
       TapDef t{p[0], p[1], p[2]};
       if (t.group >= NUM_GROUPS || t.column >= c.group_size[t.group]) fail("tap out of range");
+      if (t.back >= MAX_TAP_BACK) fail("tap reaches too far back");      // halo = 4 * back words per staged column; rv32im taps reach back <= 5
       if (i) {
         const TapDef& q = c.taps.back();
         if (std::tie(q.group, q.column, q.back) >= std::tie(t.group, t.column, t.back)) fail("taps must be strictly sorted by (group, column, back)");

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <fcntl.h>
 #include <cerrno>
 #include <fstream>
 #include <sstream>
@@ -41,6 +42,7 @@ struct Api {
   decltype(&nvrtcGetProgramLogSize) getLogSize;
   decltype(&nvrtcGetProgramLog) getLog;
   decltype(&nvrtcDestroyProgram) destroyProgram;
+  decltype(&nvrtcVersion) version = nullptr;
   CUresult (*moduleLoadData)(CUmodule*, const void*);
   CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*);
   CUresult (*moduleUnload)(CUmodule);
@@ -67,6 +69,7 @@ Api& api() {
     a.getLogSize = (decltype(a.getLogSize))sym(rt, "nvrtcGetProgramLogSize");
     a.getLog = (decltype(a.getLog))sym(rt, "nvrtcGetProgramLog");
     a.destroyProgram = (decltype(a.destroyProgram))sym(rt, "nvrtcDestroyProgram");
+    a.version = (decltype(a.version))dlsym(rt, "nvrtcVersion");
     a.ok = all;
     void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
     if (!cu) { a.cu_why = "libcuda.so.1 not loadable"; return; }
@@ -485,35 +488,102 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
   return o.str();
 }
 
-// ZKB_CACHE_DIR, else `_jitcache/` next to libzkb200.so (so that cubins compiled at build time ship with the library),
-// else /tmp/zkb200-cache.
+// ---- on-disk cubin cache -------------------------------------------------------------------------------------------------
+// A cubin found on disk is code that will run inside the prover's CUDA context, next to the private witness, so the cache
+// follows the rules of any per-user code cache:
+//   * directory: ZKB_CACHE_DIR, else `_jitcache/` next to libzkb200.so when this user can write it (cubins compiled at build time
+//     ship with the library), else $XDG_CACHE_HOME/zkb200 or ~/.cache/zkb200 created 0700.  Never a shared /tmp path; with no
+//     usable directory the cache is memory-only.
+//   * a directory or file is trusted only if it is owned by this uid (or root) and not writable by group / others;
+//   * every file carries a header (magic, key = fnv1a64(source), a second hash over source + options + NVRTC version, payload size,
+//     payload checksum), so stale or torn files are cache misses, not load errors;
+//   * files are written to a mkstemp() name and renamed; compilation is serialised on a process-wide mutex (bench.py runs three
+//     prover threads per process); a cubin that fails to LOAD is deleted and recompiled once.
+static const char* const NVRTC_OPTS[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--restrict"};
+static bool trusted(const struct stat& st) { return (st.st_uid == geteuid() || st.st_uid == 0) && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0; }
+static bool usable_dir(const std::string& d, bool create) {
+  if (create && mkdir(d.c_str(), 0700) != 0 && errno != EEXIST) return false;
+  struct stat st;
+  if (lstat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return false;
+  return trusted(st);
+}
 static std::string cache_dir() {
   const char* e = getenv("ZKB_CACHE_DIR");
-  if (e && *e) return e;
+  if (e && *e) return usable_dir(e, true) ? std::string(e) : std::string();
   Dl_info info;
   if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
     std::string so = info.dli_fname;
     size_t slash = so.rfind('/');
     if (slash != std::string::npos) {
       std::string d = so.substr(0, slash) + "/_jitcache";
-      if (mkdir(d.c_str(), 0777) == 0 || errno == EEXIST) { if (access(d.c_str(), W_OK) == 0) return d; }
+      if (usable_dir(d, access(so.substr(0, slash).c_str(), W_OK) == 0)) return d;     // read-only installs still use the shipped cubins
     }
   }
-  return "/tmp/zkb200-cache";
+  std::string base;
+  const char* x = getenv("XDG_CACHE_HOME"); const char* h = getenv("HOME");
+  if (x && *x == '/') base = x; else if (h && *h == '/') { base = std::string(h) + "/.cache"; mkdir(base.c_str(), 0700); }
+  if (base.empty()) return std::string();
+  std::string d = base + "/zkb200";
+  return usable_dir(d, true) ? d : std::string();
 }
 static int min_blocks() { const char* e = getenv("ZKB_EC_MINBLOCKS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : v > 16 ? 16 : v; }
 
-static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
+struct CubinHeader { uint32_t magic; uint32_t version; uint64_t key; uint64_t key2; uint64_t size; uint64_t sum; };
+static constexpr uint32_t CUBIN_MAGIC = 0x4a424b5au;      // "ZKBJ"
+static uint64_t fnv1a_bytes(const char* p, size_t n, uint64_t h = 1469598103934665603ull) { for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; } return h; }
+static uint64_t second_key(const std::string& src) {
+  int maj = 0, min = 0; if (api().version) api().version(&maj, &min);
+  std::string salt = "zkb200-jit-v2|nvrtc " + std::to_string(maj) + "." + std::to_string(min);
+  for (const char* o : NVRTC_OPTS) { salt += '|'; salt += o; }
+  uint64_t h = fnv1a_bytes(salt.data(), salt.size(), 0x9e3779b97f4a7c15ull);
+  return fnv1a_bytes(src.data(), src.size(), h) ^ (uint64_t)src.size();
+}
+static std::string cubin_path(const std::string& dir, uint64_t key) {
+  char name[64]; snprintf(name, sizeof name, "/ec_%016llx_sm100a.zkbj", (unsigned long long)key);
+  return dir + name;
+}
+static bool cache_read(const std::string& path, uint64_t key, uint64_t key2, std::vector<char>& cubin) {
+  int fd = open(path.c_str(), O_RDONLY | O_NOFOLLOW | O_CLOEXEC);
+  if (fd < 0) return false;
+  struct stat st; CubinHeader h;
+  bool ok = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && trusted(st) && (size_t)st.st_size > sizeof h && read(fd, &h, sizeof h) == (ssize_t)sizeof h &&
+            h.magic == CUBIN_MAGIC && h.version == 2 && h.key == key && h.key2 == key2 && h.size == (uint64_t)st.st_size - sizeof h;
+  if (ok) {
+    cubin.resize((size_t)h.size);
+    size_t got = 0;
+    while (got < cubin.size()) { ssize_t r = read(fd, cubin.data() + got, cubin.size() - got); if (r <= 0) break; got += (size_t)r; }
+    ok = got == cubin.size() && fnv1a_bytes(cubin.data(), cubin.size()) == h.sum;
+  }
+  close(fd);
+  if (!ok) cubin.clear();
+  return ok;
+}
+static void cache_write(const std::string& dir, const std::string& path, uint64_t key, uint64_t key2, const std::vector<char>& cubin) {
+  std::string tmpl = dir + "/.ec_tmp_XXXXXX";
+  std::vector<char> tmp(tmpl.begin(), tmpl.end()); tmp.push_back('\0');
+  int fd = mkstemp(tmp.data());          // unique per call (threads, processes, ranks), created 0600
+  if (fd < 0) return;
+  CubinHeader h{CUBIN_MAGIC, 2, key, key2, (uint64_t)cubin.size(), fnv1a_bytes(cubin.data(), cubin.size())};
+  bool ok = write(fd, &h, sizeof h) == (ssize_t)sizeof h && write(fd, cubin.data(), cubin.size()) == (ssize_t)cubin.size();
+  ok = (fchmod(fd, 0644) == 0) && ok;
+  close(fd);
+  if (!ok || rename(tmp.data(), path.c_str()) != 0) unlink(tmp.data());
+}
+
+static std::mutex g_compile_mutex;
+static bool compile(const std::string& src, std::vector<char>& cubin, std::string& why, bool ignore_disk = false) {
+  std::lock_guard<std::mutex> lock(g_compile_mutex);
   Api& a = api();
-  const uint64_t key = fnv1a(src);
-  char name[64]; snprintf(name, sizeof name, "/ec_%016llx_sm100a.cubin", (unsigned long long)key);
-  const std::string path = cache_dir() + name;
-  { std::ifstream f(path, std::ios::binary);
-    if (f) { cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>()); if (!cubin.empty()) return true; } }
+  const uint64_t key = fnv1a(src), key2 = second_key(src);
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? std::string() : cubin_path(dir, key);
+  if (!path.empty()) {
+    if (ignore_disk) unlink(path.c_str());
+    else if (cache_read(path, key, key2, cubin)) return true;
+  }
   nvrtcProgram prog;
   if (a.createProgram(&prog, src.c_str(), "zkb_eval_check.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { why = "nvrtcCreateProgram failed"; return false; }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--restrict"};
-  nvrtcResult r = a.compileProgram(prog, 4, opts);
+  nvrtcResult r = a.compileProgram(prog, (int)(sizeof NVRTC_OPTS / sizeof NVRTC_OPTS[0]), NVRTC_OPTS);
   if (r != NVRTC_SUCCESS) {
     size_t ls = 0; a.getLogSize(prog, &ls);
     std::string log(ls, '\0'); if (ls) a.getLog(prog, &log[0]);
@@ -524,10 +594,7 @@ static bool compile(const std::string& src, std::vector<char>& cubin, std::strin
   size_t sz = 0; a.getCUBINSize(prog, &sz);
   cubin.resize(sz); a.getCUBIN(prog, cubin.data());
   a.destroyProgram(&prog);
-  mkdir(cache_dir().c_str(), 0777);
-  { std::string tmp = path + ".tmp" + std::to_string((long)getpid());
-    std::ofstream f(tmp, std::ios::binary);
-    if (f) { f.write(cubin.data(), (std::streamsize)cubin.size()); f.close(); rename(tmp.c_str(), path.c_str()); } }
+  if (!path.empty()) cache_write(dir, path, key, key2, cubin);
   return true;
 }
 
@@ -574,6 +641,11 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool s
   if (!compile(src, cubin, why)) { cache->failed[key] = true; return nullptr; }
   ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
+  if (r != CUDA_SUCCESS) {      // a cached cubin that does not load (other driver, damaged file) is a cache miss: drop it, recompile once
+    cubin.clear();
+    if (!compile(src, cubin, why, /*ignore_disk=*/true)) { cache->failed[key] = true; return nullptr; }
+    r = a.moduleLoadData(&k.mod, cubin.data());
+  }
   if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
   if (r == CUDA_SUCCESS && k.smem > 48 * 1024) r = a.funcSetAttribute(k.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k.smem);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleLoadData: ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }

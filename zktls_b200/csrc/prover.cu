@@ -228,9 +228,10 @@ struct zkb_prover {
     po2 = po2_; n = (size_t)1 << po2;
     iop->commit(hash_protocol_info((const uint8_t*)PROOF_SYSTEM_INFO));
     iop->commit(hash_protocol_info(circuit.info));
+    for (uint32_t i = 0; i < circuit.out_size; ++i) ZKB_REQUIRE(h_io[i] < P, "io word is not a canonical field element (must be < P)");
     io.assign(h_io, h_io + circuit.out_size);
     std::vector<uint32_t> hdr(io);
-    hdr.push_back(Fp::from((uint32_t)po2).v);
+    hdr.push_back((uint32_t)po2);      // risc0 prove_segment appends Elem::from_u32_slice(&[po2]): the RAW word (a bytemuck cast), not enc(po2)
     iop->commit(hash_words(hdr.data(), hdr.size()));
     iop->write(hdr.data(), hdr.size());
     commit_group(GROUP_CODE, code, on_device);
@@ -474,6 +475,8 @@ zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const vo
   ZKB_API_BEGIN
   ZKB_REQUIRE(p != nullptr, "null prover");
   use(p->ctx);
+  ZKB_REQUIRE((h_io || p->circuit.out_size == 0) && (code || p->circuit.group_size[GROUP_CODE] == 0) && (data || p->circuit.group_size[GROUP_DATA] == 0) &&
+              (accum || p->circuit.group_size[GROUP_ACCUM] == 0), "null argument");
   p->segment_begin(po2, h_io, code, data, traces_on_device != 0, nullptr);
   p->segment_finish(accum, traces_on_device != 0);
   ZKB_API_END

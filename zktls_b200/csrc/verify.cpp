@@ -107,7 +107,22 @@ static Digest hash_protocol_info(const uint8_t* info) {
   return hash_words(e, 16);
 }
 
-static void verify_segment(const CircuitDef& c, const uint32_t* seal, size_t seal_words) {
+// check_code: risc0-zkp `Verifier::verify(.., check_code: impl Fn(u32, &Digest) -> Result<..>)` -- the code group's Merkle root IS the
+// program being proven (its "control ID" for this po2).  Without this binding a prover may choose the code trace freely; in
+// the SYN family an all-zero selector column makes every constraint vanish, so a seal for ANY claimed io would verify.
+struct ControlCheck {
+  const uint32_t* ids; size_t n;      // n entries of 9 words: po2, code root[8]
+  uint32_t* out;                      // 9 words (po2, code root) handed back to the caller, or nullptr
+  void operator()(uint32_t po2, const Digest& root) const {
+    if (out) { out[0] = po2; memcpy(out + 1, root.w, 32); }
+    if (n == 0) { VFY(out != nullptr, "no control ID to check the code root against"); return; }
+    for (size_t i = 0; i < n; ++i)
+      if (ids[9 * i] == po2 && memcmp(ids + 9 * i + 1, root.w, 32) == 0) return;
+    VFY(false, "code root is not a control ID of this circuit for this po2 (check_code)");
+  }
+};
+
+static void verify_segment(const CircuitDef& c, const uint32_t* seal, size_t seal_words, const ControlCheck& check_code) {
   ReadIOP iop(seal, seal_words);
   // header (App. D.2)
   iop.commit(hash_protocol_info((const uint8_t*)PROOF_SYSTEM_INFO));
@@ -115,11 +130,12 @@ static void verify_segment(const CircuitDef& c, const uint32_t* seal, size_t sea
   const uint32_t* hdr = iop.read_fp(c.out_size + 1);
   iop.commit(hash_words(hdr, c.out_size + 1));
   const uint32_t* out_g = hdr;
-  const uint32_t po2 = Fp::raw(hdr[c.out_size]).as_u32();
+  const uint32_t po2 = hdr[c.out_size];      // the raw word (`to_u32_words()[0]`), as the prover wrote it
   VFY(po2 >= 1 && po2 + 2 <= (uint32_t)MAX_PO2, "po2 out of range");
   const size_t n = (size_t)1 << po2, domain = n * INV_RATE;
   // group commitments: code, data, then the mix globals, then accum (commit order of prove_segment)
   MerkleVerifier code_m(iop, domain, c.group_size[GROUP_CODE]);
+  check_code(po2, code_m.root());
   MerkleVerifier data_m(iop, domain, c.group_size[GROUP_DATA]);
   std::vector<uint32_t> mix_g(c.mix_size);
   for (uint32_t i = 0; i < c.mix_size; ++i) mix_g[i] = iop.rng.random_elem().v;
@@ -244,11 +260,15 @@ using namespace zkb;
 
 extern "C" {
 
-zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words) {
+zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words,
+                           const uint32_t* h_control_ids, size_t n_control_ids, uint32_t* h_out_po2_code_root) {
   ZKB_API_BEGIN
   ZKB_REQUIRE(h_circuit && h_seal, "null argument");
+  ZKB_REQUIRE(h_control_ids || n_control_ids == 0, "null control ID table");
+  ZKB_REQUIRE(n_control_ids > 0 || h_out_po2_code_root,
+              "zkb_verify_segment needs the circuit's control IDs (po2, code root), or an output buffer so the caller can check the code root itself");
   CircuitDef c = CircuitDef::parse(h_circuit, circuit_words);
-  verify_segment(c, h_seal, seal_words);
+  verify_segment(c, h_seal, seal_words, ControlCheck{h_control_ids, n_control_ids, h_out_po2_code_root});
   ZKB_API_END
 }
 

@@ -80,6 +80,28 @@ class SegmentProver:
         r = np.zeros(n.value * 8, np.uint32); check(lib().zkb_prover_roots_copy(self.h, _hp(r))); return r.reshape(n.value, 8)
 
 
-def verify_segment(circuit_blob, seal):
+def control_id(po2, code_root):
+    """One control-ID entry (po2, code root[8]) for verify_segment: the Merkle root of the code group identifies the program
+    (risc0-zkp `check_code(po2, root)`); `code_root` is `roots()[0]` of a prover that committed the genuine code trace."""
+    return np.concatenate([np.array([po2], np.uint32), np.ascontiguousarray(code_root, dtype=np.uint32).ravel()[:8]])
+
+
+def verify_segment(circuit_blob, seal, control_ids):
+    """Raises ZkbError unless `seal` verifies AND its code root is one of `control_ids` (array of 9-word entries, see
+    control_id()).  Returns (po2, code_root)."""
     blob = np.ascontiguousarray(circuit_blob, dtype=np.uint32); seal = np.ascontiguousarray(seal, dtype=np.uint32)
-    check(lib().zkb_verify_segment(_hp(blob), _sz(blob.size), _hp(seal), _sz(seal.size)))
+    ids = np.ascontiguousarray(control_ids, dtype=np.uint32).ravel()
+    if ids.size == 0 or ids.size % 9:
+        raise ValueError("control_ids must hold 9-word entries (po2, code root[8])")
+    out = np.zeros(9, np.uint32)
+    check(lib().zkb_verify_segment(_hp(blob), _sz(blob.size), _hp(seal), _sz(seal.size), _hp(ids), _sz(ids.size // 9), _hp(out)))
+    return int(out[0]), out[1:].copy()
+
+
+def seal_code_root(circuit_blob, seal):
+    """(po2, code root) a seal commits to, with every other check of verify_segment applied -- for building a control-ID table
+    from a trusted seal; NOT a verification of the program."""
+    blob = np.ascontiguousarray(circuit_blob, dtype=np.uint32); seal = np.ascontiguousarray(seal, dtype=np.uint32)
+    out = np.zeros(9, np.uint32)
+    check(lib().zkb_verify_segment(_hp(blob), _sz(blob.size), _hp(seal), _sz(seal.size), None, _sz(0), _hp(out)))
+    return int(out[0]), out[1:].copy()
