@@ -35,7 +35,13 @@ METRIC = "segments proven/sec (2^20 cycles)"
 UNIT = "segments/s"
 PO2 = 20
 P = 2013265921
-INT32_MODMUL_PEAK = 3.27e12     # measured: tools/ubench/fp64_mix.cu, INT32-only row (11.25 modmul/clk/SM at 1965 MHz)
+# Multiplier-pipe ("fmaheavy") model of sm_100a, fitted to ncu (profiles/r1_v_hash_ncu_raw.txt: sm__pipe_fmaheavy_cycles_active
+# 88.5 % = 7327 model slots / 8279 slot-times per permutation; tools/sass_hist.py reproduces the 7327 from the SASS): the pipe has
+# 16 lanes per SM sub-partition (64 per SM); IMAD / IMAD.IADD occupy one slot, IMAD.WIDE / IMAD.HI two.
+FMAHEAVY_LANES_PER_SM = 64
+SLOTS_MONT, SLOTS_SHOUP = 5, 4                      # Montgomery product = WIDE + IMAD + HI; Shoup product = HI + 2 IMAD
+SLOTS_PER_PERMUTATION = 852 * SLOTS_MONT + 504 * SLOTS_SHOUP      # 6276: the multiplications alone (1356 modmul)
+SLOTS_PER_BUTTERFLY = SLOTS_SHOUP                   # Shoup twiddle product; the add / sub run on the ALU pipe
 
 
 def load_peaks():
@@ -95,6 +101,9 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None}
 
 
+_TRACES = {}
+
+
 def cpu_baseline(sample_po2, threads=None):
     """The oracle prover (restated CpuHal) on a SYN-280 segment of 2^sample_po2 cycles, all host threads."""
     from zktls_b200 import circuit, synth
@@ -106,38 +115,49 @@ def cpu_baseline(sample_po2, threads=None):
     O.lib().orc_set_num_threads(int(threads) if threads else (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()))
     cores = O.lib().orc_num_threads()
     blob = circuit.syn_circuit(**circuit.SYN280).blob()
-    io, code, data, accum = synth.trace_a(circuit.SYN280, sample_po2, 0xB200)
+    if sample_po2 not in _TRACES:                      # generated once per size (1.17 GB at 2^20), outside every timed region
+        _TRACES.clear()
+        _TRACES[sample_po2] = synth.trace_a(circuit.SYN280, sample_po2, 0xB200)
+    io, code, data, accum = _TRACES[sample_po2]
     t0 = time.time()
     pr = O.Prover(blob)
     pr.begin(sample_po2, io, code, data)
     pr.finish(accum)
     dt = time.time() - t0
-    scale = 1 << (PO2 - sample_po2)
-    return dt, cores, dt * scale
+    return dt, cores
 
 
 def reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The Rust crates cannot be built here (no
-    cargo, source un-vendored), so this is the oracle port (oracle/, C++/OpenMP restatement of CpuHal)."""
+    cargo, source un-vendored), so this is the oracle port (oracle/, C++/OpenMP restatement of CpuHal) on all host threads.
+    Every timed step proves one REAL SYN-280 segment of 2^20 cycles (no extrapolation): `value` = segments / measured seconds.
+    A full segment takes 20-40 s on a GPU box's host cores, so the number of timed steps is capped by a wall-clock budget
+    (--ref-budget-s, default 150 s; at least one step): `steps` is what was timed, `steps_requested` what the command line asked."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_po2 = args.cpu_sample_po2 or 16
+    po2 = args.po2
+    warm = []
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(min(sample_po2, 12))
-    times = []
-    cores = 0
-    for _ in range(args.steps):
-        dt, cores, full = cpu_baseline(sample_po2)
-        times.append(full)
+        warm.append(cpu_baseline(min(po2, 14))[0])             # untimed: loads the library, spins up the OpenMP team
+    times, cores = [], 0
+    t_start = time.time()
+    while len(times) < max(1, args.steps):
+        dt, cores = cpu_baseline(po2)
+        times.append(dt)
+        if (time.time() - t_start) + dt > args.ref_budget_s:      # the next step would not fit
+            break
     ms = 1000.0 * sum(times) / len(times)
     value = 1000.0 / ms
-    sample = f"SYN-280 segment of 2^{sample_po2} cycles per step, time x{1 << (PO2 - sample_po2)} (work is linear in rows up to the log factor of the NTTs)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    sample = (f"{len(times)} full SYN-280 segment(s) of 2^{po2} cycles proven by the oracle prover (C++/OpenMP restatement of CpuHal), "
+              f"{', '.join(f'{t:.1f}' for t in times)} s each; measured, not extrapolated")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps,
+            "warmup": min(args.warmup, 1), "warmup_requested": args.warmup, "warmup_what": "one 2^14-cycle segment (library load + OpenMP team), untimed",
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
-            "config": workload_config(),
+            "config": workload_config(po2),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "steps_capped_by": None if len(times) >= args.steps else f"--ref-budget-s {args.ref_budget_s:.0f} (a full CPU segment proof takes {ms / 1000:.0f} s)"}
     print(json.dumps(line), flush=True)
 
 
@@ -158,10 +178,12 @@ def pin_rank_to_gpu_numa_node(index):
         pass
 
 
-def workload_config():
-    return {"workload": "syn280-segment-po2-20: one synthetic 2^20-cycle rv32im-shaped segment (BASELINE.json configs[1]): iNTT+zk-shift, x4 LDE, "
+def workload_config(po2=PO2):
+    """identical in both arms (the driver compares the two `config` objects)"""
+    name = "syn280-segment-po2-20" if po2 == PO2 else f"DEBUG po2={po2} (not the benchmark config)"
+    return {"workload": name + ": one synthetic 2^20-cycle rv32im-shaped segment (BASELINE.json configs[1]): iNTT+zk-shift, x4 LDE, "
                         "Poseidon2 Merkle commit of code/data/accum/check, eval_check, DEEP + mix + divide, 3 FRI rounds, 50 queries; seal on host",
-            "po2": PO2, "columns": {"accum": 40, "code": 16, "data": 224, "check": 16}, "trace": "A (uniform field elements, seeded)",
+            "po2": po2, "columns": {"accum": 40, "code": 16, "data": 224, "check": 16}, "trace": "A (uniform field elements, seeded)",
             "l2": "inputs (1.17 GB trace, 4.7 GB LDE) exceed the 126 MB L2, no flush needed", "parallelism": "segment-parallel, one process per GPU, no data-path collective"}
 
 
@@ -172,7 +194,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--po2", type=int, default=PO2, help="debug only: any value other than 20 is not the benchmark config")
-    ap.add_argument("--cpu-sample-po2", type=int, default=0)
+    ap.add_argument("--cpu-sample-po2", type=int, default=0, help="cpu_baseline leg of the GPU arm: prove a 2^k-cycle segment instead of the full 2^20 one (debug)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget for the timed full-size CPU segment proofs (at least one is run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=3, help="segments proven concurrently per GPU (one host thread + stream each)")
     ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
@@ -245,20 +268,22 @@ def main():
     torch.cuda.synchronize()
 
     def run_workers(fn, k):
-        """segments 0..k-1 over the `inflight` workers (worker w takes w, w + inflight, ...); returns the last seal of worker 0"""
+        """segments 0..k-1 over the `inflight` workers (worker w takes w, w + inflight, ...); returns the last seal a worker produced"""
         out, errs = [None] * inflight, []
         def work(w):
             try:
                 out[w] = fn(w, len(range(w, k, inflight)))
             except Exception as e:      # noqa: BLE001
                 errs.append(e)
+                for ev in first_up:     # nobody may wait for a worker that died
+                    ev.set()
         ths = [threading.Thread(target=work, args=(w,)) for w in range(1, inflight)]
         for th in ths: th.start()
         work(0)
         for th in ths: th.join()
         if errs:
             raise errs[0]
-        return out[0]
+        return next((o for o in out if o is not None), None)
 
     def device_worker(w, k):
         s = None
@@ -266,24 +291,55 @@ def main():
             s = provers[w].prove(po2, io, *bufs[w])
         return s
 
-    def host_worker(w, k):
-        """k segments from HOST (pinned) buffers through the C-ABI, double-buffered: the 1.17 GB upload of segment i+1 runs on
-        the copy stream while segment i is proven (what a session's queue of continuation segments does).  Every segment's
-        host->device copy and seal read-back happen inside this call."""
+    class SegmentQueue:
+        """k segments handed to whichever worker asks next (a session's continuation segments are a queue, not a static split:
+        the tail is then one segment, not one round of `inflight`)."""
+        def __init__(self, k):
+            self.left, self.lock = k, threading.Lock()
+        def take(self):
+            with self.lock:
+                if self.left <= 0:
+                    return False
+                self.left -= 1
+                return True
+
+    def host_worker(w, queue):
+        """Segments from HOST (pinned) buffers through the C-ABI, double-buffered: the 1.17 GB upload of the worker's next segment
+        runs on the copy stream while the current one is proven.  Every segment's host->device copy and seal read-back happen
+        inside this call.  A proof starts as soon as its 64 MB code group has landed (per-group upload events inside
+        zkb_prove_staged); the data / accum uploads run behind the first commits."""
         s = None
-        if k:
-            # the workers' FIRST uploads take turns on the PCIe link (worker w starts when worker w-1's has landed); after
-            # that every upload hides behind a proof
+        have = queue.take()
+        if have:
+            # the workers' FIRST uploads take turns on the PCIe link (worker w starts when worker w-1's has landed) instead of
+            # splitting it three ways; after that every upload hides behind a proof.  A helper thread waits for the upload so
+            # that this thread can already be proving (zkb_prover_stage_wait only synchronises the copy stream).
             if w > 0:
                 first_up[w - 1].wait()
             provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
-            provers[w].stage_wait()
-        first_up[w].set()
-        for i in range(k):
-            if i + 1 < k:
+            entered = threading.Event()
+            def landed():
+                entered.set()
+                provers[w].stage_wait()
+                first_up[w].set()
+            threading.Thread(target=landed, daemon=True).start()
+            entered.wait()
+        else:
+            first_up[w].set()
+        while have:
+            nxt = queue.take()
+            if nxt:
                 provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
             s = provers[w].prove_staged(io)
+            have = nxt
         return s
+
+    def run_host(k):
+        q = SegmentQueue(k)
+        out = run_workers(lambda w, _k: host_worker(w, q), inflight)       # one call per worker; the queue decides who proves what
+        return out
+
+    first_up = [threading.Event() for _ in range(inflight)]
 
     # ---- device-resident arm -----------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank); sampler.start()
@@ -307,11 +363,11 @@ def main():
 
     # ---- end-to-end arm: host buffers through the C-ABI prove call ------------------------------------------------------
     first_up = [threading.Event() for _ in range(inflight)]
-    seal_h = run_workers(host_worker, min(args.warmup, 2) * inflight)
+    seal_h = run_host(min(args.warmup, 2) * inflight)
     barrier()
     first_up = [threading.Event() for _ in range(inflight)]
     hal.timer_start()
-    seal_h = run_workers(host_worker, args.steps)
+    seal_h = run_host(args.steps)
     ms_e2e = hal.timer_stop()
     barrier()
     t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
@@ -329,7 +385,7 @@ def main():
         first_up = [threading.Event() for _ in range(inflight)]
         barrier()
         hal.timer_start(); ts0 = time.time()
-        run_workers(host_worker, mine)
+        run_host(mine)
         ms_sess = hal.timer_stop()
         barrier()
         t = torch.tensor([ms_sess], device=dev, dtype=torch.float64)
@@ -342,6 +398,8 @@ def main():
     roof = None
     if rank == 0:
         peaks, peak_kind = load_peaks()
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0          # the clock observed during the timed region
+        slot_peak = FMAHEAVY_LANES_PER_SM * hal.device_info()["sm_count"] * sm_mhz * 1e6      # multiplier-pipe issue slots per second
         rows, cols = 4 * n, shape["data_cols"]
         mat = hal.alloc_elem(rows * cols)           # contents irrelevant for timing; zero-initialised
         dig = hal.alloc_digest(rows)
@@ -353,9 +411,10 @@ def main():
             hal.hash_rows(dig, mat)
         ms = hal.timer_stop() / reps
         alg_bytes = 4 * rows * cols + 32 * rows
-        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        hbm_achieved = alg_bytes / (ms * 1e-3) / 1e9
         perms = rows * ((cols + 15) // 16)
-        traffic, traffic_src, ncu_pipes = None, None, None
+        slots = perms * SLOTS_PER_PERMUTATION / (ms * 1e-3)
+        traffic, traffic_src, ncu_pipes, stale = None, None, None, None
         import glob
         tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_hash_rows_traffic.json")))     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture per round
         tpath = tpaths[-1] if tpaths else ""
@@ -364,15 +423,19 @@ def main():
                 tj = json.load(f)
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
             ncu_pipes = {k: tj[k] for k in ("sm__pipe_fmaheavy_cycles_active_pct", "sm__pipe_alu_cycles_active_pct", "smsp__issue_active_pct") if k in tj}
-        roof = {"bound": "hbm", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
-                "peak_source": peak_kind, "ms_per_launch": ms,
-                "int32": {"note": "Poseidon2 is INT32-pipe bound, not HBM bound (SURVEY.md 8d): 1356 modmul per permutation; peak = measured "
-                                  "pure Montgomery-modmul stream on B200 (profiles/r1_ubench_fp64_mix.txt)",
-                          "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3), "peak_modmul_per_s": INT32_MODMUL_PEAK,
-                          "frac": 1356 * perms / (ms * 1e-3) / INT32_MODMUL_PEAK, "ncu_pipe_utilisation": ncu_pipes}}
+            if tj.get("duration_ms"):               # the capture is of another build if its kernel time is far from today's
+                stale = abs(tj["duration_ms"] - ms) / ms > 0.10
+        roof = {"bound": "int32", "kernel": "k_hash_rows (Poseidon2, 224 cols x 2^22 rows)",
+                "achieved": slots / 1e12, "peak": slot_peak / 1e12, "unit": "T multiplier-pipe slots/s", "frac": slots / slot_peak,
+                "what": "Poseidon2 is bound by the INT32 multiplier (fmaheavy) pipe, not HBM (SURVEY.md 8d).  achieved = permutations/s x 6276 slots "
+                        "(852 Montgomery products x 5 + 504 Shoup products x 4: the multiplications alone); peak = 64 lanes/SM x SMs x the SM clock "
+                        "observed in the timed region.  Slot costs (IMAD 1, IMAD.WIDE / IMAD.HI 2) are fitted to ncu's sm__pipe_fmaheavy_cycles_active.",
+                "sm_mhz": sm_mhz, "permutations_per_s": perms / (ms * 1e-3), "modmul_per_s": 1356 * perms / (ms * 1e-3), "ms_per_launch": ms,
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_stale": stale, "ncu_pipe_utilisation": ncu_pipes,
+                "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
+                        "algorithmic_bytes": alg_bytes, "peak_source": peak_kind}}
         del mat, dig
-        # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT and x4 LDE over 64 columns of 2^20
+        # NTT roofline lines (BASELINE metric "NTT GB/s"): iNTT + zk-shift and x4 LDE over the data group's 224 columns of 2^20
         ntt_cols = 224
         buf = hal.alloc_elem(ntt_cols * n); big = hal.alloc_elem(ntt_cols * 4 * n)
         for _ in range(2):
@@ -387,30 +450,31 @@ def main():
         ms_l = hal.timer_stop() / reps
         mm_i = ntt_cols * (n // 2) * po2 + ntt_cols * n            # butterflies + inter-pass twiddle / scale multiplications
         mm_l = ntt_cols * 2 * n * po2 + ntt_cols * 4 * n
-        roof["ntt"] = {"intt_zk_shift": {"cols": ntt_cols, "po2": po2, "ms": ms_i, "GBps": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9, "frac": 8 * n * ntt_cols / (ms_i * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                         "int32_frac": mm_i / (ms_i * 1e-3) / INT32_MODMUL_PEAK},
-                       "lde_x4": {"cols": ntt_cols, "po2": po2, "ms": ms_l, "GBps": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9, "frac": 20 * n * ntt_cols / (ms_l * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                  "int32_frac": mm_l / (ms_l * 1e-3) / INT32_MODMUL_PEAK},
-                       "note": "NTT GB/s on algorithmic bytes (8 n c / 20 n c); above n ~ 2^12 the butterflies are INT32-pipe bound, hence int32_frac"}
+        def ntt_line(ms_, alg, mm):
+            return {"cols": ntt_cols, "po2": po2, "ms": ms_, "GBps": alg / (ms_ * 1e-3) / 1e9, "hbm_frac": alg / (ms_ * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "int32_frac": mm * SLOTS_PER_BUTTERFLY / (ms_ * 1e-3) / slot_peak}
+        roof["ntt"] = {"intt_zk_shift": ntt_line(ms_i, 8 * n * ntt_cols, mm_i), "lde_x4": ntt_line(ms_l, 20 * n * ntt_cols, mm_l),
+                       "note": "NTT GB/s on algorithmic bytes (8 n c / 20 n c); int32_frac = butterflies x 4 multiplier-pipe slots (one Shoup twiddle product) "
+                               "against the same hardware slot peak: above n ~ 2^12 the transform is bound by that pipe, not by HBM"}
         del buf, big
 
-    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only): ONE full 2^20 segment, measured -----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_po2 = args.cpu_sample_po2 or 17
-        dt, cores, full = cpu_baseline(sample_po2)
-        cpu = {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle prover (C++/OpenMP restatement of CpuHal) on one SYN-280 segment of 2^{sample_po2} cycles: {dt:.2f} s, x{1 << (PO2 - sample_po2)} for 2^20"}
+        sample_po2 = args.cpu_sample_po2 or po2
+        dt, cores = cpu_baseline(sample_po2)
+        scale = 1 << (po2 - sample_po2)
+        cpu = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle prover (C++/OpenMP restatement of CpuHal) on one SYN-280 segment of 2^{sample_po2} cycles: {dt:.2f} s"
+                         + ("; the full benchmark segment, measured" if scale == 1 else f", x{scale} for 2^{po2} (DEBUG sample)")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
-                "config": dict(workload_config(), segments_in_flight_per_gpu=inflight), "clocks": clocks,
+                "config": workload_config(po2), "segments_in_flight_per_gpu": inflight, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k"},
                 "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
-        if po2 != PO2:
-            line["config"]["workload"] = f"DEBUG po2={po2} (not the benchmark config)"
         print(json.dumps(line), flush=True)
     for pr in provers:
         pr.close()

@@ -164,7 +164,8 @@ zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const vo
 zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, const void* h_data, const void* h_accum);
 zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io);
 /* Blocks until every upload started by zkb_prover_stage_traces on this prover has landed (lets several provers that share
- * one PCIe link take turns instead of splitting its bandwidth). */
+ * one PCIe link take turns instead of splitting its bandwidth).  It only synchronises the prover's copy stream, so -- unlike
+ * every other call on a prover -- it may run on another host thread while zkb_prove_staged is in progress. */
 zkb_err zkb_prover_stage_wait(zkb_prover* p);
 /* CPU verifier for a seal produced by the prover (risc0-zkp verify/*): checks the transcript, Merkle paths, FRI
  * and the constraint relation at the DEEP point.  Host-only, like the reference's verifier.

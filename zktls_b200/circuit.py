@@ -97,3 +97,81 @@ def syn_circuit(accum_cols=40, code_cols=16, data_cols=224, mix_size=20, out_siz
 
 
 SYN280 = dict(accum_cols=40, code_cols=16, data_cols=224, mix_size=20, out_size=32)
+
+
+def syn_heavy_circuit(accum_cols=40, code_cols=16, data_cols=224, mix_size=20, out_size=32, majors=16, fanout=(4, 4, 2), leaf_constraints=40, seed=0x5EA7):
+    """SYN-HEAVY: an eval_check stress circuit with the SHAPE of rv32im's generated `poly_fp` (hard part 4; VERDICT r1
+    next #5) on the SYN-280 column layout: by default 16 x 4 x 4 x 2 = 512 leaf blocks of 40 constraints = 20,480 constraints plus the
+    selector constraints, > 100 k `PolyExtStep`s, total degree 5, `AndCond` nested four deep (major / minor / sub / leaf selectors taken
+    from code columns at back 0 and 2), taps back 0..4 on a third of the data and half of the accum columns, back {0,1,3} / {0,1} on
+    the rest, {0,2} on four code columns => five combos.  Constraint operands are drawn pseudo-randomly over ALL columns and taps
+    (every column is read hundreds of times, from every part of the program), which is what defeats a streaming column ring.
+    Deterministic in `seed`.  The constraints are not meant to be satisfiable: parity and timing use uniform traces (Trace A)."""
+    import random
+    rnd = random.Random(seed)
+    b = CircuitBuilder(accum_cols, code_cols, data_cols, mix_size, out_size, info=("SYNHEAVY%d:v1" % (accum_cols + code_cols + data_cols)).ljust(16, "_").encode()[:16])
+    backs = {}
+    for c in range(accum_cols):
+        backs[(GROUP_ACCUM, c)] = (0, 1, 2, 3, 4) if c % 2 == 0 else (0, 1)
+    for c in range(code_cols):
+        backs[(GROUP_CODE, c)] = (0, 2) if c < 4 else (0,)
+    for c in range(data_cols):
+        backs[(GROUP_DATA, c)] = ((0, 1, 2, 3, 4), (0, 1), (0, 1, 3))[c % 3]
+    for (g, c), bs in backs.items():
+        for k in bs:
+            b.add_tap(g, c, k)
+    b.finish_taps()
+    cols = sorted(backs)
+    cache = {}
+
+    def tap(g, c, k):
+        if (g, c, k) not in cache:
+            cache[(g, c, k)] = b.get(g, c, k)
+        return cache[(g, c, k)]
+
+    def any_tap():
+        g, c = cols[rnd.randrange(len(cols))]
+        return tap(g, c, rnd.choice(backs[(g, c)]))
+
+    def leaf_constraint(chain):
+        # degree-1 relation over 3..4 taps and a global: a - (b + k * c) [- m]   (total degree 5 under four selectors)
+        a, x, y = any_tap(), any_tap(), any_tap()
+        k = b.const(rnd.randrange(1, 1 << 20))
+        e = b.sub(a, b.add(x, b.mul(k, y)))
+        if rnd.random() < 0.3:
+            e = b.sub(e, b.get_global(GLOBAL_MIX, rnd.randrange(mix_size)) if rnd.random() < 0.5 else b.get_global(GLOBAL_OUT, rnd.randrange(out_size)))
+        return b.and_eqz(chain, e)
+
+    def selector(level, idx):
+        c = (level * 3 + idx) % code_cols
+        return tap(GROUP_CODE, c, 2 if (c < 4 and (idx & 1)) else 0)
+
+    top = b.true()
+    one = b.const(1)
+    for c in range(code_cols):          # selectors are bits: degree-2 constraints at the top level
+        s = tap(GROUP_CODE, c, 0)
+        top = b.and_eqz(top, b.mul(s, b.sub(s, one)))
+    # a few degree-4 / degree-3 relations at shallow depth (products of taps), like the memory / multiply constraints of rv32im
+    shallow = b.true()
+    for _ in range(64):
+        shallow = b.and_eqz(shallow, b.sub(b.mul(b.mul(any_tap(), any_tap()), b.mul(any_tap(), any_tap())), any_tap()))
+    top = b.and_cond(top, selector(0, 0), shallow)
+    for mj in range(majors):
+        lvl1 = b.true()
+        for mn in range(fanout[0]):
+            lvl2 = b.true()
+            for sb in range(fanout[1]):
+                lvl3 = b.true()
+                for lf in range(fanout[2]):
+                    leaf = b.true()
+                    for _ in range(leaf_constraints):
+                        leaf = leaf_constraint(leaf)
+                    lvl3 = b.and_cond(lvl3, selector(3, mj + mn + sb + lf), leaf)
+                lvl2 = b.and_cond(lvl2, selector(2, mj + mn + sb), lvl3)
+            lvl1 = b.and_cond(lvl1, selector(1, mj + mn), lvl2)
+        top = b.and_cond(top, selector(0, mj + 1), lvl1)
+    b.ret = top
+    return b
+
+
+SYNHEAVY = dict(SYN280)

@@ -144,27 +144,33 @@ struct zkb_prover {
   struct TraceSlot {
     uint32_t* buf[3] = {nullptr, nullptr, nullptr};
     size_t words[3] = {0, 0, 0};
-    cudaEvent_t uploaded = nullptr, consumed = nullptr;
+    cudaEvent_t uploaded[3] = {nullptr, nullptr, nullptr};      // one per trace group: a group's commit starts as soon as ITS bytes have landed
+    cudaEvent_t consumed = nullptr;
     int po2 = -1;
     bool full = false;
   };
   TraceSlot slots[2];
   cudaStream_t copy_stream = nullptr;
   int stage_idx = 0, prove_idx = 0;
+  const cudaEvent_t* group_ready = nullptr;      // staged proof in progress: per-group upload events the commits wait on
 
   void stage_traces(int po2_, const void* const h_traces[3]) {
     ZKB_REQUIRE(po2_ >= 6 && po2_ + 2 <= MAX_PO2, "segment po2 out of range [6, 24]");
     if (!copy_stream) ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     TraceSlot& sl = slots[stage_idx];
     ZKB_REQUIRE(!sl.full, "both staging slots are full: call zkb_prove_staged first");
-    if (!sl.uploaded) {
-      ZKB_CUDA(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+    if (!sl.consumed) {
+      for (int g = 0; g < 3; ++g) ZKB_CUDA(cudaEventCreateWithFlags(&sl.uploaded[g], cudaEventDisableTiming));
       ZKB_CUDA(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
     } else {
       ZKB_CUDA(cudaStreamWaitEvent(copy_stream, sl.consumed, 0));    // the proof that last read this slot must be done with it
     }
     const size_t rows = (size_t)1 << po2_;
-    for (int g = 0; g < 3; ++g) {
+    // in commit order (code, data, accum): the proof of this segment can start when the 64 MB code group is in, and the data /
+    // accum uploads run behind its first commits instead of in front of them
+    static const int ORDER[3] = {GROUP_CODE, GROUP_DATA, GROUP_ACCUM};
+    for (int k = 0; k < 3; ++k) {
+      const int g = ORDER[k];
       size_t words = (size_t)circuit.group_size[g] * rows;
       if (sl.words[g] < words) {
         if (sl.buf[g]) { ZKB_CUDA(cudaStreamSynchronize(ctx->stream)); ZKB_CUDA(cudaStreamSynchronize(copy_stream)); ZKB_CUDA(cudaFree(sl.buf[g])); }
@@ -172,15 +178,16 @@ struct zkb_prover {
         sl.words[g] = words;
       }
       if (words) ZKB_CUDA(cudaMemcpyAsync(sl.buf[g], h_traces[g], words * 4, cudaMemcpyHostToDevice, copy_stream));
+      ZKB_CUDA(cudaEventRecord(sl.uploaded[g], copy_stream));
     }
-    ZKB_CUDA(cudaEventRecord(sl.uploaded, copy_stream));
     sl.po2 = po2_; sl.full = true;
     stage_idx ^= 1;
   }
   void prove_staged(const uint32_t* h_io) {
     TraceSlot& sl = slots[prove_idx];
     ZKB_REQUIRE(sl.full, "no staged traces: call zkb_prover_stage_traces first");
-    ZKB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.uploaded, 0));
+    struct Guard { const cudaEvent_t*& r; ~Guard() { r = nullptr; } } guard{group_ready};      // also on an error path
+    group_ready = sl.uploaded;
     segment_begin(sl.po2, h_io, sl.buf[GROUP_CODE], sl.buf[GROUP_DATA], true, nullptr);
     segment_finish(sl.buf[GROUP_ACCUM], true);
     ZKB_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
@@ -190,7 +197,7 @@ struct zkb_prover {
   void free_staging() {
     for (TraceSlot& sl : slots) {
       for (int g = 0; g < 3; ++g) { if (sl.buf[g]) cudaFree(sl.buf[g]); sl.buf[g] = nullptr; sl.words[g] = 0; }
-      if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+      for (int g = 0; g < 3; ++g) if (sl.uploaded[g]) cudaEventDestroy(sl.uploaded[g]);
       if (sl.consumed) cudaEventDestroy(sl.consumed);
       sl = TraceSlot();
     }
@@ -209,6 +216,7 @@ struct zkb_prover {
   void commit_group(int g, const void* trace, bool on_device) {
     PhaseTimer pt(ctx);
     size_t cols = circuit.group_size[g];
+    if (group_ready) ZKB_CUDA(cudaStreamWaitEvent(ctx->stream, group_ready[g], 0));
     DevBuf c(ctx, cols * n);
     // a trace that is already on the device is read in place by the first iNTT pass (no device-to-device copy)
     if (cols && !on_device) ZKB_CUDA(cudaMemcpyAsync(c.p, trace, cols * n * 4, cudaMemcpyHostToDevice, ctx->stream));
