@@ -199,6 +199,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=3, help="segments proven concurrently per GPU (one host thread + stream each)")
     ap.add_argument("--breakdown", action="store_true", help="per-operator timings to stderr")
+    ap.add_argument("--workload", default="syn280", choices=["syn280", "synheavy"],
+                    help="syn280 = the benchmark segment (BASELINE configs[1]); synheavy = the SAME segment shape with the rv32im-shaped SYN-HEAVY "
+                         "constraint system (22 k constraints, 117 k steps): a SECONDARY, eval_check-weighted line, not the headline")
     ap.add_argument("--session-segments", type=int, default=64, help="segments of the synthetic TLS session timed for the 'e2e TLS prove s' metric (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -244,7 +247,8 @@ def main():
     po2 = args.po2
     n = 1 << po2
     shape = circuit.SYN280
-    blob = circuit.syn_circuit(**shape).blob()
+    heavy = args.workload == "synheavy"
+    blob = (circuit.syn_heavy_circuit() if heavy else circuit.syn_circuit(**shape)).blob()
     # `inflight` segments are proven concurrently per GPU, each by its own host thread + ctx (stream) + prover: one segment's
     # latency-bound stretches (Merkle tree tops, FRI rounds, Fiat-Shamir round trips) are filled by the other's kernels
     # (">= 2 segments in flight per GPU").  A ctx is used by one thread at a time, as the C-ABI requires.
@@ -460,13 +464,31 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only): ONE full 2^20 segment, measured -----------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not heavy:
         sample_po2 = args.cpu_sample_po2 or po2
         dt, cores = cpu_baseline(sample_po2)
         scale = 1 << (po2 - sample_po2)
         cpu = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle prover (C++/OpenMP restatement of CpuHal) on one SYN-280 segment of 2^{sample_po2} cycles: {dt:.2f} s"
                          + ("; the full benchmark segment, measured" if scale == 1 else f", x{scale} for 2^{po2} (DEBUG sample)")}
+
+    ec = None
+    if rank == 0 and heavy:      # eval_check alone over the 2^22-point domain, CUDA events
+        dom = 4 * n
+        bufs_ec = [hal.alloc_elem(shape[k] * dom) for k in ("accum_cols", "code_cols", "data_cols")]
+        chk = hal.alloc_elem(4 * dom)
+        gl_m, gl_o, pm = np.arange(1, 1 + shape["mix_size"], dtype=np.uint32), np.arange(1, 1 + shape["out_size"], dtype=np.uint32), np.arange(3, 7, dtype=np.uint32)
+        for _ in range(2):
+            hal.eval_check(chk, blob, *bufs_ec, gl_m, gl_o, pm, po2)
+        hal.timer_start()
+        for _ in range(3):
+            hal.eval_check(chk, blob, *bufs_ec, gl_m, gl_o, pm, po2)
+        ms_ec = hal.timer_stop() / 3
+        n_eqz = int((blob[16 + 3 * int(blob[6]):].reshape(-1, 4)[:, 0] == circuit.OP_AND_EQZ).sum())
+        ec = {"kernel": "zkb_ec (flat form: all tapped columns resident per 128-point tile, PTX units)", "ms": ms_ec, "constraints": n_eqz, "steps": int(blob[7]),
+              "domain_points": dom, "constraint_evaluations_per_s": n_eqz * dom / (ms_ec * 1e-3),
+              "multiplier_slots_per_point": n_eqz * (4 * 2 + 5), "note": "per constraint: 4 IMAD.WIDE accumulations (8 slots) + ~1 Montgomery product (5 slots) on the multiplier pipe"}
+        del bufs_ec, chk
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -475,6 +497,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k"},
                 "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
+        if heavy:
+            line["config"]["workload"] = "SECONDARY synheavy280-segment-po2-20: the benchmark segment's shape (280 columns, 2^20 cycles, Trace A) under the SYN-HEAVY " \
+                                         "constraint system (rv32im-shaped: 22 k constraints / 117 k PolyExtSteps, AndCond depth 4, taps back 0..4, 5 combos) -- eval_check-weighted companion of the headline"
+            line["eval_check"] = ec
         print(json.dumps(line), flush=True)
     for pr in provers:
         pr.close()

@@ -42,6 +42,8 @@ zkb_err zkb_init_on_stream(int device, void* cuda_stream, zkb_ctx** out);   /* b
 zkb_err zkb_destroy(zkb_ctx* ctx);
 zkb_err zkb_sync(zkb_ctx* ctx);
 zkb_err zkb_device_info(zkb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* CUDA devices visible to this process (segments are sharded over them, one ctx per device and worker: no ctx needed) */
+zkb_err zkb_device_count(int* out);
 /* number of kernels this ctx has launched so far (bench.py's `gpu_launches`) */
 zkb_err zkb_kernel_launches(zkb_ctx* ctx, uint64_t* out);
 /* CUDA-event timer on the ctx stream (the stream the kernels are launched on) */
@@ -124,10 +126,12 @@ zkb_err zkb_eval_check(zkb_ctx* ctx, void* d_check, const uint32_t* h_circuit, s
                        const void* d_code, const void* d_data, const uint32_t* h_mix_g, const uint32_t* h_out_g,
                        const uint32_t* h_poly_mix, int po2);
 
-/* The specialised (NVRTC-compiled) form of eval_check for a circuit: its generated CUDA source (host-only; writes up to
- * cap bytes NUL-terminated, full length to *needed), and an ahead-of-time compile into the on-disk cubin cache
- * (ZKB_CACHE_DIR, default /tmp/zkb200-cache) -- the counterpart of the reference compiling its generated poly_fp at
- * crate build time. */
+/* The specialised (JIT-compiled) form of eval_check for a circuit: its generated source (host-only; writes up to cap bytes
+ * NUL-terminated, full length to *needed) -- CUDA C++ for ordinary circuits, a CUDA C++ tile kernel + PTX unit functions for
+ * heavy ones (>= 2000 constraints: the "flat" form, linked with nvJitLink) -- and an ahead-of-time compile into the on-disk cubin
+ * cache: ZKB_CACHE_DIR, else `_jitcache/` next to the library, else $XDG_CACHE_HOME/zkb200 or ~/.cache/zkb200 (0700); directories
+ * and files must be owned by the user (or root) and not group/world-writable; never a shared /tmp path.  The counterpart of the
+ * reference compiling its generated poly_fp at crate build time. */
 zkb_err zkb_eval_check_source(const uint32_t* h_circuit, size_t circuit_words, char* out, size_t cap, size_t* needed);
 zkb_err zkb_eval_check_precompile(const uint32_t* h_circuit, size_t circuit_words);
 /* CircuitHal::accumulate(ctrl, io, data, mix, accum, steps) (risc0-circuit-rv32im `prove/hal/{cpu,cuda}.rs`, run by

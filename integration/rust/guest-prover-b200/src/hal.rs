@@ -4,10 +4,10 @@
 use std::{cell::RefCell, ffi::c_void, marker::PhantomData, rc::Rc};
 
 use risc0_core::field::baby_bear::{BabyBear, BabyBearElem, BabyBearExtElem};
-use risc0_zkp::{core::{digest::Digest, log2_ceil}, hal::{Buffer, Hal}};
+use risc0_zkp::{core::{digest::Digest, hash::{poseidon2::Poseidon2HashSuite, HashSuite}, log2_ceil}, hal::{Buffer, Hal}};
 use zkb200_sys as sys;
 
-fn ok(e: sys::ZkbErr) { sys::ffi_wrap(|| e).unwrap_or_else(|m| panic!("zkb200: {m}")) }
+pub(crate) fn ok(e: sys::ZkbErr) { sys::ffi_wrap(|| e).unwrap_or_else(|m| panic!("zkb200: {m}")) }
 
 struct Raw { ctx: *mut sys::ZkbCtx, ptr: *mut c_void, bytes: usize }
 impl Drop for Raw { fn drop(&mut self) { unsafe { sys::zkb_free(self.ctx, self.ptr); } } }
@@ -40,10 +40,12 @@ impl<T: Clone + bytemuck::Pod> B200Buffer<T> {
     }
 }
 
-pub struct B200Hal { pub(crate) ctx: *mut sys::ZkbCtx }
+/// `suite`: the `poseidon2` hash suite (host-side hashing of small inputs + the Fiat-Shamir rng; the device kernels implement the same
+/// permutation -- libzkb200 has no other suite, which is why there is no `B200Hal<Hash>` type parameter like `CudaHal<CH>`).
+pub struct B200Hal { pub(crate) ctx: *mut sys::ZkbCtx, suite: HashSuite<BabyBear> }
 
 impl B200Hal {
-    pub fn new(device: i32) -> Self { let mut ctx = std::ptr::null_mut(); ok(unsafe { sys::zkb_init(device, &mut ctx) }); Self { ctx } }
+    pub fn new(device: i32) -> Self { let mut ctx = std::ptr::null_mut(); ok(unsafe { sys::zkb_init(device, &mut ctx) }); Self { ctx, suite: Poseidon2HashSuite::new_suite() } }
     fn alloc<T: Clone + bytemuck::Pod>(&self, size: usize) -> B200Buffer<T> {
         let bytes = (size * std::mem::size_of::<T>()).max(16); let mut p = std::ptr::null_mut();
         ok(unsafe { sys::zkb_alloc(self.ctx, bytes, &mut p) }); ok(unsafe { sys::zkb_memset0(self.ctx, p, bytes) });
@@ -60,7 +62,7 @@ impl Hal for B200Hal {
     type Field = BabyBear; type Elem = BabyBearElem; type ExtElem = BabyBearExtElem; type Buffer<T: Clone + bytemuck::Pod> = B200Buffer<T>;
 
     fn has_unified_memory(&self) -> bool { false }
-    fn get_hash_suite(&self) -> &risc0_zkp::core::hash::HashSuite<BabyBear> { &crate::POSEIDON2_SUITE }
+    fn get_hash_suite(&self) -> &HashSuite<BabyBear> { &self.suite }
 
     fn alloc_elem(&self, _n: &'static str, size: usize) -> Self::Buffer<Self::Elem> { self.alloc(size) }
     fn alloc_extelem(&self, _n: &'static str, size: usize) -> Self::Buffer<Self::ExtElem> { self.alloc(size) }

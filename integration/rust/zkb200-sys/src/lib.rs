@@ -16,6 +16,7 @@ extern "C" {
     pub fn zkb_destroy(ctx: *mut ZkbCtx) -> ZkbErr;
     pub fn zkb_sync(ctx: *mut ZkbCtx) -> ZkbErr;
     pub fn zkb_device_info(ctx: *mut ZkbCtx, sm_count: *mut c_int, cc_major: *mut c_int, cc_minor: *mut c_int, total_mem: *mut usize) -> ZkbErr;
+    pub fn zkb_device_count(out: *mut c_int) -> ZkbErr;
     pub fn zkb_kernel_launches(ctx: *mut ZkbCtx, out: *mut u64) -> ZkbErr;
     pub fn zkb_timer_start(ctx: *mut ZkbCtx) -> ZkbErr;
     pub fn zkb_timer_stop(ctx: *mut ZkbCtx, ms: *mut f32) -> ZkbErr;

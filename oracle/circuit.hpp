@@ -31,6 +31,7 @@ struct Circuit {
   std::vector<std::vector<uint32_t>> combos;   // lexicographically sorted distinct back-lists
   std::vector<Step> steps;
   size_t n_fp_vars = 0, n_mix_vars = 0;
+  std::vector<Step> wsteps;      // witness ("accumulate") program, DESIGN.md "circuit blob"
 
   size_t tap_size() const { return taps.size(); }
   size_t combos_size() const { return combos.size(); }
@@ -42,10 +43,10 @@ struct Circuit {
     Circuit c;
     for (int g = 0; g < 3; ++g) c.group_size[g] = w[1 + g];
     c.mix_size = w[4]; c.out_size = w[5];
-    size_t n_taps = w[6], n_steps = w[7];
+    size_t n_taps = w[6], n_steps = w[7], n_wsteps = w[11];
     c.ret = w[8];
     for (int i = 0; i < 16; ++i) c.info[i] = (uint8_t)(w[12 + i / 4] >> (8 * (i % 4)));
-    if (len != CIRCUIT_HEADER_WORDS + 3 * n_taps + 4 * n_steps) throw std::runtime_error("circuit blob: bad length");
+    if (len != CIRCUIT_HEADER_WORDS + 3 * n_taps + 4 * n_steps + 4 * n_wsteps) throw std::runtime_error("circuit blob: bad length");
     const uint32_t* p = w + CIRCUIT_HEADER_WORDS;
     for (size_t i = 0; i < n_taps; ++i, p += 3) {
       Tap t{p[0], p[1], p[2]};
@@ -87,9 +88,64 @@ struct Circuit {
       c.steps.push_back(s);
     }
     if (c.ret >= c.n_mix_vars) throw std::runtime_error("circuit blob: ret out of range");
+    for (size_t i = 0; i < n_wsteps; ++i, p += 4) c.wsteps.push_back(Step{p[0], p[1], p[2], p[3]});      // witness program: checked where it is run
     return c;
   }
 };
+
+// Witness program interpreter: CircuitHal::accumulate as data (risc0-circuit-rv32im `prove/hal/cpu.rs` accumulate: the circuit's
+// generated step_compute_accum run over every cycle, then Hal::prefix_products).  Phases (separated by Barrier / PrefixProduct) run
+// one after the other, rows within a phase independently; a phase reads accum columns only as earlier phases (or the caller) left them.
+enum : uint32_t { W_CONST = 0, W_GET = 1, W_GET_GLOBAL = 2, W_ADD = 3, W_SUB = 4, W_MUL = 5, W_SET = 6, W_BARRIER = 7, W_PREFIX_PRODUCT = 8 };
+static void accumulate(const Circuit& c, Fp* accum, const Fp* code, const Fp* data, const Fp* mix_g, const Fp* out_g, int po2) {
+  const size_t n = (size_t)1 << po2;
+  const Fp* groups[3] = {accum, code, data};
+  size_t lo = 0, first_val = 0;
+  while (lo < c.wsteps.size()) {
+    size_t hi = lo;
+    while (hi < c.wsteps.size() && c.wsteps[hi].op != W_BARRIER && c.wsteps[hi].op != W_PREFIX_PRODUCT) ++hi;
+    size_t n_vals = 0;
+    for (size_t k = lo; k < hi; ++k) n_vals += c.wsteps[k].op <= W_MUL;
+    // sets are buffered per phase so that a row never sees another row's write of the same phase, whatever the parser allowed
+    std::vector<std::pair<size_t, Fp>> writes;
+#pragma omp parallel
+    {
+      std::vector<Fp> v(n_vals);
+      std::vector<std::pair<size_t, Fp>> mine;
+#pragma omp for schedule(static)
+      for (long long row = 0; row < (long long)n; ++row) {
+        size_t vi = 0;
+        for (size_t k = lo; k < hi; ++k) {
+          const Step& s = c.wsteps[k];
+          auto val = [&](uint32_t id) -> Fp { if (id < first_val || id - first_val >= vi) throw std::runtime_error("witness operand outside its phase"); return v[id - first_val]; };
+          switch (s.op) {
+            case W_CONST: v[vi++] = Fp::from(s.a); break;
+            case W_GET: v[vi++] = groups[s.a][(size_t)s.b * n + (((size_t)row + n - (s.c % n)) & (n - 1))]; break;
+            case W_GET_GLOBAL: v[vi++] = s.a == 0 ? mix_g[s.b] : out_g[s.b]; break;
+            case W_ADD: v[vi++] = val(s.a) + val(s.b); break;
+            case W_SUB: v[vi++] = val(s.a) - val(s.b); break;
+            case W_MUL: v[vi++] = val(s.a) * val(s.b); break;
+            case W_SET: if (s.c == 0xffffffffu || val(s.c).v != 0) mine.emplace_back((size_t)s.a * n + (size_t)row, val(s.b)); break;
+            default: throw std::runtime_error("bad witness opcode");
+          }
+        }
+      }
+#pragma omp critical
+      writes.insert(writes.end(), mine.begin(), mine.end());
+    }
+    for (auto& w : writes) accum[w.first] = w.second;
+    first_val += n_vals;
+    if (hi < c.wsteps.size() && c.wsteps[hi].op == W_PREFIX_PRODUCT) {      // 4 planar accum columns = one Fp4 column: inclusive product scan
+      Fp* col = accum + (size_t)c.wsteps[hi].a * n;
+      Fp4 cur = Fp4::one();
+      for (size_t i = 0; i < n; ++i) {
+        cur *= Fp4(col[i], col[n + i], col[2 * n + i], col[3 * n + i]);
+        col[i] = cur.c[0]; col[n + i] = cur.c[1]; col[2 * n + i] = cur.c[2]; col[3 * n + i] = cur.c[3];
+      }
+    }
+    lo = hi + 1;
+  }
+}
 
 struct MixState { Fp4 tot, mul; };
 

@@ -32,7 +32,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.orc_seal_words.restype = C.c_size_t
         _lib.orc_root_count.restype = C.c_size_t
-        for name in ("orc_eval_check", "orc_prover_new", "orc_segment_begin", "orc_segment_finish", "orc_verify_segment"):
+        for name in ("orc_eval_check", "orc_accumulate", "orc_prover_new", "orc_segment_begin", "orc_segment_finish", "orc_verify_segment"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_void_p
         _lib.orc_rng_new.restype = C.c_void_p
@@ -215,6 +215,13 @@ def eval_check(blob, accum, code, data, mix_g, out_g, poly_mix, po2):
     blob = u32(blob); check = np.zeros(16 << po2, np.uint32)
     _check(lib().orc_eval_check(_p(check), _p(blob), _sz(blob.size), _p(u32(accum)), _p(u32(code)), _p(u32(data)), _p(u32(mix_g)), _p(u32(out_g)), _p(u32(poly_mix)), C.c_int(po2)))
     return check
+
+
+def accumulate(blob, accum, code, data, mix_g, out_g, po2):
+    """CircuitHal::accumulate: runs the circuit blob's witness program over `accum` (returns the new accum group)."""
+    blob = u32(blob); accum = u32(accum).copy()
+    _check(lib().orc_accumulate(_p(blob), _sz(blob.size), _p(accum), _p(u32(code)), _p(u32(data)), _p(u32(mix_g)), _p(u32(out_g)), C.c_int(po2)))
+    return accum
 
 
 class Prover:

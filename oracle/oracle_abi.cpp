@@ -94,6 +94,14 @@ const char* orc_eval_check(uint32_t* check, const uint32_t* blob, size_t blob_wo
   ORC_END
 }
 
+const char* orc_accumulate(const uint32_t* blob, size_t blob_words, uint32_t* accum, const uint32_t* code, const uint32_t* data,
+                           const uint32_t* mix_g, const uint32_t* out_g, int po2) {
+  ORC_TRY
+  Circuit c = Circuit::parse(blob, blob_words);
+  accumulate(c, (Fp*)accum, (const Fp*)code, (const Fp*)data, (const Fp*)mix_g, (const Fp*)out_g, po2);
+  ORC_END
+}
+
 const char* orc_prover_new(const uint32_t* blob, size_t blob_words, void** out) {
   ORC_TRY
   std::unique_ptr<OrcProver> p(new OrcProver);

@@ -56,3 +56,27 @@ def test_generated_rust_bindings_are_current():
     src, names = mod.generate()
     assert sorted(names) == header_symbols()
     assert open(os.path.join(ROOT, "integration", "rust", "zkb200-sys", "src", "lib.rs")).read() == src, "run python tools/gen_rust_ffi.py"
+
+
+def test_rust_integration_tree_is_self_consistent():
+    """integration/rust is source only (no Rust toolchain here), but it must not dangle: every `crate::x::y` path used under
+    guest-prover-b200/src resolves to a module file that defines `y`, every `mod x;` has its file, every zkb200_sys / sys:: call
+    names a function the generated bindings declare, and the CLI patch touches the reference files VERDICT r1 listed."""
+    src = os.path.join(ROOT, "integration", "rust", "guest-prover-b200", "src")
+    files = {f[:-3]: open(os.path.join(src, f)).read() for f in os.listdir(src) if f.endswith(".rs")}
+    for name, text in files.items():
+        for m in re.findall(r"^\s*pub mod (\w+);", text, flags=re.M):
+            assert m in files, f"{name}.rs declares mod {m} but src/{m}.rs is missing"
+        for mod, item in re.findall(r"crate::(\w+)::(\w+)", text):
+            assert mod in files, f"{name}.rs uses crate::{mod} but src/{mod}.rs is missing"
+            assert re.search(rf"\b(fn|struct|trait|const|static|enum|type)\s+{item}\b", files[mod]), f"crate::{mod}::{item} (used in {name}.rs) is not defined"
+        assert not re.search(r"crate::[A-Z_]{3,}\b", text), f"{name}.rs refers to a crate-level static that does not exist"
+    bindings = open(os.path.join(ROOT, "integration", "rust", "zkb200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (zkb_\w+)\(", bindings)) | {"ffi_wrap"}
+    for name, text in files.items():
+        for fn in re.findall(r"(?:sys|zkb200_sys)::(zkb_\w+|ffi_wrap)", text):
+            assert fn in declared, f"{name}.rs calls {fn}, which zkb200-sys does not declare"
+    patch = open(os.path.join(ROOT, "integration", "patches", "0001-bins-zktls-add-b200-backend.patch")).read()
+    for touched in ("bins/zktls/src/commands/types.rs", "bins/zktls/src/commands/prove.rs", "bins/zktls/Cargo.toml"):
+        assert f"+++ b/{touched}" in patch
+    assert "B200," in patch and "b200-backend" in patch and "B200GuestProver" in patch

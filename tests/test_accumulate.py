@@ -38,10 +38,46 @@ def test_accumulate_matches_host_witness_generator(hal, shape, po2):
     assert np.array_equal(got.reshape(-1, n)[:, ~live], noise.reshape(-1, n)[:, ~live]), "rows outside the selector must be left alone"
 
 
+def _grand_product_circuit():
+    """a witness program the SYN family does not have: an unconditional Set from taps at back 0 / 2, a barrier, a second phase
+    that reads the first phase's column at back 1, and a PrefixProduct over four accum columns (a grand-product column)"""
+    from zktls_b200.circuit import CircuitBuilder, GROUP_ACCUM, GROUP_CODE, GROUP_DATA, GLOBAL_MIX, GLOBAL_OUT
+    b = CircuitBuilder(6, 2, 3, 2, 2, info=b"GRANDPROD:v1____")
+    for g, n in ((GROUP_ACCUM, 6), (GROUP_CODE, 2), (GROUP_DATA, 3)):
+        for c in range(n):
+            b.add_tap(g, c, 0)
+    b.finish_taps()
+    b.ret = b.and_eqz(b.true(), b.sub(b.get(GROUP_ACCUM, 0, 0), b.get(GROUP_ACCUM, 0, 0)))
+    m0, m1 = b.w_get_global(GLOBAL_MIX, 0), b.w_get_global(GLOBAL_MIX, 1)
+    for k in range(4):                                   # columns 0..3 = (m0 + d0[i] * d1[i-2] + k, ...): the factors of the grand product
+        v = b.w_add(b.w_add(m0, b.w_mul(b.w_get(GROUP_DATA, 0, 0), b.w_get(GROUP_DATA, 1, 2))), b.w_const(k + 1))
+        b.w_set(k, b.w_mul(v, m1) if k == 3 else v)
+    b.w_barrier()
+    prev = b.w_get(GROUP_ACCUM, 1, 1)                    # phase 2 reads what phase 1 wrote, one row back
+    b.w_set(4, b.w_sub(prev, b.w_get_global(GLOBAL_OUT, 1)), b.w_get(GROUP_CODE, 0, 0))
+    b.w_prefix_product(0)                                # columns 0..3 become the running product over the rows
+    b.w_set(5, b.w_add(b.w_get(GROUP_ACCUM, 0, 0), b.w_get(GROUP_ACCUM, 3, 1)))          # phase 3 reads the scanned columns
+    return b
+
+
+@pytest.mark.parametrize("po2", [5, 9, 13])
+def test_accumulate_program_with_prefix_product_matches_oracle(hal, oracle, po2):
+    b = _grand_product_circuit(); blob = b.blob()
+    rng = np.random.default_rng(po2)
+    n = 1 << po2
+    accum, code, data = (oracle.random_fp(rng, c * n) for c in b.group_size)
+    code[:n] = oracle.encode(rng.integers(0, 2, size=n))      # the condition column: zeros and ones
+    mix, io = oracle.random_fp(rng, 2), oracle.random_fp(rng, 2)
+    want = oracle.accumulate(blob, accum, code, data, mix, io, po2)
+    d_accum = hal.copy_from_elem(accum)
+    hal.accumulate(blob, d_accum, hal.copy_from_elem(code), hal.copy_from_elem(data), mix, io, po2)
+    assert np.array_equal(d_accum.to_numpy(), want)
+
+
 def test_accumulate_is_rejected_for_a_circuit_without_a_witness_program(hal):
     from zktls_b200._lib import ZkbError
     b = circuit.syn_circuit(**SMALL)
-    b.info = b"RV32IM:v1_______"
+    b.wsteps = []                       # a blob without a witness program (e.g. exported from a circuit whose accumulate stays on the host)
     blob = b.blob()
     buf = hal.alloc_elem(4 << 6)
     with pytest.raises(ZkbError, match="no witness program"):

@@ -1,0 +1,122 @@
+"""eval_check on circuits with the SHAPE of rv32im's generated poly_fp (SYN-HEAVY: > 20 k constraints, > 10^5 PolyExtSteps, AndCond
+nested four deep, taps back 0..4, five combos; zktls_b200/circuit.py) -- the flat form of the JIT (all tapped columns resident in
+shared memory, constraint tree flattened into (condition product) x poly_mix^k x value terms, units emitted as PTX and linked with
+nvJitLink; csrc/k_eval_jit.cu) against the CPU oracle.  VERDICT r1 next #5."""
+import numpy as np
+import pytest
+
+from zktls_b200 import circuit, synth
+
+P = 2013265921
+REDUCED = dict(accum_cols=6, code_cols=6, data_cols=12, mix_size=5, out_size=4, majors=3, fanout=(2, 2, 2), leaf_constraints=12)
+
+
+def test_heavy_circuit_has_the_advertised_shape():
+    b = circuit.syn_heavy_circuit()
+    eqz = sum(1 for s in b.steps if s[0] == circuit.OP_AND_EQZ)
+    assert eqz >= 20000 and len(b.steps) >= 80000
+    backs = {}
+    for g, c, k in b.taps:
+        backs.setdefault((g, c), []).append(k)
+    combos = {tuple(v) for v in backs.values()}
+    assert len(combos) >= 5 and (0, 1, 2, 3, 4) in combos
+    assert sum(1 for v in backs.values() if max(v) == 4) >= len(backs) // 3
+    # AndCond nesting depth
+    depth, mi, best = {}, 0, 0
+    for op, a, b_, c in b.steps:
+        if op < circuit.OP_TRUE:
+            continue
+        d = 0 if op == circuit.OP_TRUE else depth[a] if op == circuit.OP_AND_EQZ else max(depth[a], depth[c] + 1)
+        depth[mi] = d; best = max(best, d); mi += 1
+    assert best >= 4
+
+
+def test_flat_source_is_ptx_units_plus_a_resident_tile_kernel(monkeypatch, tmp_path):
+    """CPU: the generator picks the flat form for a heavy circuit, and (when NVRTC + nvJitLink are present) it compiles and links."""
+    import ctypes as C
+    from zktls_b200 import lib
+    from zktls_b200._lib import check, ZkbError
+    monkeypatch.setenv("ZKB_CACHE_DIR", str(tmp_path))
+    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+    blob = circuit.syn_heavy_circuit(**REDUCED).blob()
+    bp = blob.ctypes.data_as(C.POINTER(C.c_uint32))
+    need = C.c_size_t()
+    check(lib().zkb_eval_check_source(bp, C.c_size_t(blob.size), None, C.c_size_t(0), C.byref(need)))
+    out = C.create_string_buffer(need.value + 1)
+    check(lib().zkb_eval_check_source(bp, C.c_size_t(blob.size), out, C.c_size_t(need.value + 1), C.byref(need)))
+    src = out.value.decode()
+    assert ".visible .func" in src and "mad.wide.u32" in src and "ld.shared.u32" in src          # units: PTX
+    assert "extern \"C\" __device__ uint4 zkb_u0" in src and "copy_col(" in src and "switch (grp)" in src      # kernel: tile load + warp groups
+    try:
+        check(lib().zkb_eval_check_precompile(bp, C.c_size_t(blob.size)))
+    except ZkbError as e:
+        if "not loadable" in str(e) or "unavailable" in str(e):
+            pytest.skip(str(e))
+        raise
+    import os
+    assert [f for f in os.listdir(tmp_path) if f.endswith(".zkbj")]
+
+
+@pytest.fixture(scope="module")
+def hal():
+    from zktls_b200.hal import B200Hal
+    h = B200Hal(0)
+    yield h
+    h.close()
+
+
+def _eval_both(hal, oracle, b, po2, seed):
+    blob = b.blob()
+    rng = np.random.default_rng(seed)
+    dom = 4 << po2
+    accum, code, data = (oracle.random_fp(rng, n * dom) for n in b.group_size)
+    mix, out, pm = oracle.random_fp(rng, b.mix_size), oracle.random_fp(rng, b.out_size), oracle.random_fp(rng, 4)
+    chk = hal.alloc_elem(4 * dom)
+    hal.eval_check(chk, blob, hal.copy_from_elem(accum), hal.copy_from_elem(code), hal.copy_from_elem(data), mix, out, pm, po2)
+    return chk.to_numpy(), oracle.eval_check(blob, accum, code, data, mix, out, pm, po2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("po2,env", [(5, {}), (6, {}), (8, {}), (8, {"ZKB_EC_FLAT_GROUPS": "1"}), (8, {"ZKB_EC_FLAT_GROUPS": "3", "ZKB_EC_UNIT": "16"}), (9, {"ZKB_EC_FLAT_POINTS": "64"})])
+def test_flat_form_matches_oracle_on_a_reduced_heavy_circuit(hal, oracle, po2, env, monkeypatch):
+    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, want = _eval_both(hal, oracle, circuit.syn_heavy_circuit(**REDUCED), po2, 500 + po2)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_flat_form_agrees_with_the_other_forms_on_syn280(hal, oracle, monkeypatch):
+    """the benchmark circuit through the flat form (it normally takes the staged form): same check polynomial"""
+    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+    got, want = _eval_both(hal, oracle, circuit.syn_circuit(**circuit.SYN280), 7, 77)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.slow
+@pytest.mark.parametrize("po2", [8, 12])
+def test_syn_heavy_matches_oracle(hal, oracle, po2):
+    """the full SYN-HEAVY circuit (22 k constraints, 117 k steps) at po2 8 and 12: 2^10 and 2^14 domain points x 117 k steps on the oracle"""
+    got, want = _eval_both(hal, oracle, circuit.syn_heavy_circuit(), po2, 900 + po2)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_segment_seal_with_a_heavy_circuit_matches_oracle(hal, oracle, monkeypatch):
+    """whole prover with a flat-form eval_check and five combos (register sizes 1, 2, 3, 5: poly_interpolate beyond the linear case)"""
+    from zktls_b200.prover import SegmentProver
+    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+    b = circuit.syn_heavy_circuit(**REDUCED)
+    blob = b.blob()
+    shape = dict(accum_cols=6, code_cols=6, data_cols=12, out_size=4)
+    po2 = 9
+    io, code_m, data_m, accum_m = synth.trace_a(shape, po2, 61)
+    gp, op = SegmentProver(hal, blob), oracle.Prover(blob)
+    seal_g = gp.prove(po2, io, code_m, data_m, accum_m)
+    op.begin(po2, io, code_m, data_m)
+    seal_o = op.finish(accum_m)
+    assert np.array_equal(gp.roots(), op.roots())
+    assert np.array_equal(seal_g, seal_o)
+    gp.close()

@@ -156,6 +156,23 @@ def test_both_oracles_agree_beyond_the_goldens(oracle):
         assert eq(p1.roots(), p2.roots())
 
 
+def test_both_oracles_agree_on_a_heavy_circuit(oracle):
+    """nested AndCond four deep, five combos (registers of 1, 2, 3 and 5 taps): eval_check and the whole seal"""
+    red = dict(accum_cols=6, code_cols=6, data_cols=12, mix_size=5, out_size=4, majors=3, fanout=(2, 2, 2), leaf_constraints=12)
+    b = circuit.syn_heavy_circuit(**red); blob = b.blob()
+    rng = np.random.default_rng(5)
+    fp = lambda n: rng.integers(0, P, size=n, dtype=np.uint32)
+    po2 = 6; dom = 4 << po2
+    accum, code, data = (fp(n * dom) for n in b.group_size)
+    mix, out, pm = fp(5), fp(4), fp(4)
+    assert eq(oracle.eval_check(blob, accum, code, data, mix, out, pm, po2), O2.eval_check(blob, accum, code, data, mix, out, pm, po2))
+    shape = dict(accum_cols=6, code_cols=6, data_cols=12, out_size=4)
+    io, code_m, data_m, accum_m = synth.trace_a(shape, 8, 33)
+    p1, p2 = oracle.Prover(blob), O2.Prover(blob)
+    assert eq(p1.begin(8, io, code_m, data_m), p2.begin(8, io, code_m, data_m))
+    assert eq(p1.finish(accum_m), p2.finish(accum_m)) and eq(p1.roots(), p2.roots())
+
+
 def test_product_never_imports_oracle2():
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -63,3 +63,31 @@ def test_circuit_blob_rejects_malformed(oracle):
 def test_splitmix_is_uniform_and_deterministic():
     a = synth.splitmix_fp(7, 10000); b = synth.splitmix_fp(7, 10000)
     assert np.array_equal(a, b) and a.max() < synth.P and abs(a.mean() / synth.P - 0.5) < 0.02
+
+
+def test_oracle_accumulate_runs_the_witness_program(oracle):
+    """CircuitHal::accumulate as data: the oracle's interpreter of the blob's witness program against the numpy statement of the
+    SYN family's accumulation step (zktls_b200/synth.py), and the parser's phase rule."""
+    import numpy as np
+    from zktls_b200 import circuit, synth
+    shape = dict(accum_cols=5, code_cols=3, data_cols=6, mix_size=5, out_size=4)
+    blob = circuit.syn_circuit(**shape).blob()
+    po2, seed = 8, 3
+    n = 1 << po2
+    io, code, data = synth.trace_b_code_data(shape, po2, seed)
+    mix = synth.encode(synth.splitmix_fp(7, shape["mix_size"])).astype(np.uint32)
+    noise = synth.to_mont(synth.splitmix_fp(seed * 4 + 3, shape["accum_cols"] * n).reshape(shape["accum_cols"], n))
+    want = synth.to_mont(synth.trace_b_accum(shape, po2, seed, code, data, io, mix))
+    got = oracle.accumulate(blob, noise, synth.to_mont(code), synth.to_mont(data), mix, io, po2)
+    assert np.array_equal(got, want)
+    # the C-ABI parser refuses a phase that reads an accum column it writes (rows run in parallel on the device)
+    import ctypes as C
+    from zktls_b200 import lib
+    from zktls_b200._lib import check, ZkbError
+    import pytest
+    b = circuit.syn_circuit(**shape)
+    b.wsteps = [s for s in b.wsteps if s[0] != circuit.W_BARRIER]
+    bad = b.blob()
+    need = C.c_size_t()
+    with pytest.raises(ZkbError, match="reads an accum column it writes|writes an accum column it reads"):
+        check(lib().zkb_eval_check_source(bad.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(bad.size), None, C.c_size_t(0), C.byref(need)))

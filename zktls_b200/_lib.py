@@ -17,7 +17,7 @@ class ZkbError(RuntimeError):
 
 # every symbol include/zkb200.h declares (tests/test_abi_symbols.py checks the header against this list and the .so)
 SYMBOLS = [
-    "zkb_version", "zkb_free_error", "zkb_init", "zkb_init_on_stream", "zkb_destroy", "zkb_sync", "zkb_device_info",
+    "zkb_version", "zkb_free_error", "zkb_init", "zkb_init_on_stream", "zkb_destroy", "zkb_sync", "zkb_device_info", "zkb_device_count",
     "zkb_kernel_launches", "zkb_timer_start", "zkb_timer_stop",
     "zkb_alloc", "zkb_free", "zkb_host_alloc", "zkb_host_free", "zkb_memset0", "zkb_fill_u32", "zkb_h2d", "zkb_d2h", "zkb_d2d",
     "zkb_batch_interpolate_ntt", "zkb_zk_shift", "zkb_batch_interpolate_ntt_zk_shift", "zkb_batch_expand", "zkb_batch_evaluate_ntt",

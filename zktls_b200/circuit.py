@@ -10,6 +10,9 @@ MAGIC = 0x5A4B4331
 OP_CONST, OP_GET, OP_GET_GLOBAL, OP_ADD, OP_SUB, OP_MUL, OP_TRUE, OP_AND_EQZ, OP_AND_COND = range(9)
 GROUP_ACCUM, GROUP_CODE, GROUP_DATA = 0, 1, 2
 GLOBAL_MIX, GLOBAL_OUT = 0, 1
+# witness ("accumulate") program: the same value opcodes as PolyExtStep plus Set / Barrier / PrefixProduct (DESIGN.md "circuit blob")
+W_CONST, W_GET, W_GET_GLOBAL, W_ADD, W_SUB, W_MUL, W_SET, W_BARRIER, W_PREFIX_PRODUCT = range(9)
+W_ALWAYS = 0xFFFFFFFF
 
 
 class CircuitBuilder:
@@ -20,6 +23,7 @@ class CircuitBuilder:
         self.taps, self.steps = [], []
         self.n_fp, self.n_mix = 0, 0
         self.ret = None
+        self.wsteps, self.n_w = [], 0          # CircuitHal::accumulate as data: per-row step program over the trace domain
 
     def add_tap(self, group, column, back):
         self.taps.append((group, column, back))
@@ -44,11 +48,26 @@ class CircuitBuilder:
     def and_eqz(self, x, val): return self._mix(OP_AND_EQZ, x, val)
     def and_cond(self, x, cond, inner): return self._mix(OP_AND_COND, x, cond, inner)
 
+    # ---- witness program (CircuitHal::accumulate): values are numbered in definition order; a value may only be used inside the
+    # phase (stretch between barriers) that defines it.  Every row of the trace domain runs the same steps.
+    def _w(self, op, a=0, b=0, c=0):
+        self.wsteps.append((op, a, b, c)); self.n_w += 1; return self.n_w - 1
+
+    def w_const(self, v): return self._w(W_CONST, v % 2013265921)
+    def w_get(self, group, column, back=0): return self._w(W_GET, group, column, back)
+    def w_get_global(self, base, offset): return self._w(W_GET_GLOBAL, base, offset)
+    def w_add(self, a, b): return self._w(W_ADD, a, b)
+    def w_sub(self, a, b): return self._w(W_SUB, a, b)
+    def w_mul(self, a, b): return self._w(W_MUL, a, b)
+    def w_set(self, accum_column, value, cond=None): self.wsteps.append((W_SET, accum_column, value, W_ALWAYS if cond is None else cond))
+    def w_barrier(self): self.wsteps.append((W_BARRIER, 0, 0, 0))
+    def w_prefix_product(self, first_accum_column): self.wsteps.append((W_PREFIX_PRODUCT, first_accum_column, 0, 0))
+
     def blob(self):
         assert self.ret is not None
-        hdr = [MAGIC] + self.group_size + [self.mix_size, self.out_size, len(self.taps), len(self.steps), self.ret, self.n_fp, self.n_mix, 0]
+        hdr = [MAGIC] + self.group_size + [self.mix_size, self.out_size, len(self.taps), len(self.steps), self.ret, self.n_fp, self.n_mix, len(self.wsteps)]
         hdr += [int.from_bytes(self.info[4 * i: 4 * i + 4], "little") for i in range(4)]
-        words = hdr + [w for t in self.taps for w in t] + [w for s in self.steps for w in s]
+        words = hdr + [w for t in self.taps for w in t] + [w for s in self.steps for w in s] + [w for s in self.wsteps for w in s]
         return np.array(words, dtype=np.uint32)
 
 
@@ -93,6 +112,21 @@ def syn_circuit(accum_cols=40, code_cols=16, data_cols=224, mix_size=20, out_siz
             o = b.get_global(GLOBAL_OUT, j % out_size)
             inner = b.and_eqz(inner, b.sub(b.sub(b.sub(a, b.mul(p1, p0)), m), o))
     b.ret = b.and_cond(top, sel, inner)
+    # witness program of the accum group (what risc0's circuit crates generate as step_compute_accum): on live rows (sel != 0)
+    #   phase 0: even column j = m_{j mod M} * d_{j mod D}[i] + d_{(j+1) mod D}[i-1]
+    #   phase 1: odd column j  = a_{j-1}[i-1] * a_{j-1}[i] + m_{j mod M} + o_{j mod O}      (reads the finished even columns)
+    # the other rows keep what the caller put there (the reference fills its trailing ZK rows with noise the same way)
+    for parity in (0, 1):
+        wsel = b.w_get(GROUP_CODE, 0, 0)
+        for j in range(parity, accum_cols, 2):
+            m = b.w_get_global(GLOBAL_MIX, j % mix_size)
+            if parity == 0:
+                v = b.w_add(b.w_mul(m, b.w_get(GROUP_DATA, j % data_cols, 0)), b.w_get(GROUP_DATA, (j + 1) % data_cols, 1))
+            else:
+                v = b.w_add(b.w_add(b.w_mul(b.w_get(GROUP_ACCUM, j - 1, 1), b.w_get(GROUP_ACCUM, j - 1, 0)), m), b.w_get_global(GLOBAL_OUT, j % out_size))
+            b.w_set(j, v, wsel)
+        if parity == 0:
+            b.w_barrier()
     return b
 
 

@@ -24,6 +24,9 @@ struct TapDef { uint32_t group, column, back; };
 constexpr uint32_t MAX_TAP_BACK = 1u << 12;
 struct RegisterDef { uint32_t group, column, tap_pos, size, combo_id; };
 struct StepDef { uint32_t op, a, b, c; };
+// witness ("accumulate") program: CircuitHal::accumulate as data -- the value opcodes of PolyExtStep + Set / Barrier / PrefixProduct
+enum : uint32_t { WX_CONST = 0, WX_GET = 1, WX_GET_GLOBAL = 2, WX_ADD = 3, WX_SUB = 4, WX_MUL = 5, WX_SET = 6, WX_BARRIER = 7, WX_PREFIX_PRODUCT = 8 };
+constexpr uint32_t WX_ALWAYS = 0xffffffffu;
 
 struct CircuitDef {
   uint32_t group_size[NUM_GROUPS] = {0, 0, 0};
@@ -34,6 +37,7 @@ struct CircuitDef {
   std::vector<std::vector<uint32_t>> combos;
   std::vector<StepDef> steps;
   uint32_t n_fp_vars = 0, n_mix_vars = 0;
+  std::vector<StepDef> wsteps;      // witness program of the accum group (may be empty: the circuit then has no device-side accumulate)
 
   size_t tap_size() const { return taps.size(); }
   size_t combos_size() const { return combos.size(); }
@@ -51,7 +55,8 @@ struct CircuitDef {
     const size_t n_taps = w[6], n_steps = w[7];
     c.ret = w[8];
     for (int i = 0; i < 16; ++i) c.info[i] = (uint8_t)(w[12 + i / 4] >> (8 * (i % 4)));
-    if (len != CIRCUIT_HEADER_WORDS + 3 * n_taps + 4 * n_steps) fail("length does not match the header counts");
+    const size_t n_wsteps = w[11];
+    if (len != CIRCUIT_HEADER_WORDS + 3 * n_taps + 4 * n_steps + 4 * n_wsteps) fail("length does not match the header counts");
     const uint32_t* p = w + CIRCUIT_HEADER_WORDS;
     c.taps.reserve(n_taps);
     for (size_t i = 0; i < n_taps; ++i, p += 3) {
@@ -103,6 +108,33 @@ struct CircuitDef {
       c.steps.push_back(s);
     }
     if (c.ret >= c.n_mix_vars) fail("ret out of range");
+    // witness program: values are numbered in definition order and live inside one phase (between barriers); a phase must not
+    // read an accum column it writes (rows run in parallel)
+    {
+      uint32_t n_vals = 0, phase_first = 0;
+      std::vector<char> set_here(c.group_size[GROUP_ACCUM], 0), got_here(c.group_size[GROUP_ACCUM], 0);
+      auto val_ok = [&](uint32_t v) { return v >= phase_first && v < n_vals; };
+      for (size_t i = 0; i < n_wsteps; ++i, p += 4) {
+        StepDef s{p[0], p[1], p[2], p[3]};
+        switch (s.op) {
+          case WX_CONST: if (s.a >= P) fail("witness Const not canonical"); ++n_vals; break;
+          case WX_GET:
+            if (s.a >= NUM_GROUPS || s.b >= c.group_size[s.a] || s.c >= MAX_TAP_BACK) fail("witness Get out of range");
+            if (s.a == GROUP_ACCUM) { if (set_here[s.b]) fail("witness phase reads an accum column it writes"); got_here[s.b] = 1; }
+            ++n_vals; break;
+          case WX_GET_GLOBAL: if (s.a > 1 || s.b >= (s.a == 0 ? c.mix_size : c.out_size)) fail("witness GetGlobal out of range"); ++n_vals; break;
+          case WX_ADD: case WX_SUB: case WX_MUL: if (!val_ok(s.a) || !val_ok(s.b)) fail("witness operand outside its phase"); ++n_vals; break;
+          case WX_SET:
+            if (s.a >= c.group_size[GROUP_ACCUM] || !val_ok(s.b) || (s.c != WX_ALWAYS && !val_ok(s.c))) fail("witness Set out of range");
+            if (got_here[s.a]) fail("witness phase writes an accum column it reads");
+            set_here[s.a] = 1; break;
+          case WX_PREFIX_PRODUCT: if ((size_t)s.a + 4 > c.group_size[GROUP_ACCUM]) fail("witness PrefixProduct out of range");     // fall through: acts as a barrier
+          case WX_BARRIER: phase_first = n_vals; std::fill(set_here.begin(), set_here.end(), 0); std::fill(got_here.begin(), got_here.end(), 0); break;
+          default: fail("unknown witness opcode");
+        }
+        c.wsteps.push_back(s);
+      }
+    }
     return c;
   }
 };

@@ -80,6 +80,15 @@ zkb_err zkb_device_info(zkb_ctx* ctx, int* sm_count, int* cc_major, int* cc_mino
   if (total_mem) *total_mem = prop.totalGlobalMem;
   ZKB_API_END
 }
+zkb_err zkb_device_count(int* out) {
+  ZKB_API_BEGIN
+  ZKB_REQUIRE(out != nullptr, "null out pointer");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }      // no driver / no device: zero, not an error
+  *out = n;
+  ZKB_API_END
+}
 zkb_err zkb_kernel_launches(zkb_ctx* ctx, uint64_t* out) {
   ZKB_API_BEGIN
   ZKB_REQUIRE(ctx && out, "null argument");

@@ -1,61 +1,60 @@
-// CircuitHal::accumulate for the circuits this library carries a witness program for.
+// CircuitHal::accumulate: the circuit's witness program for the accum group, delivered as DATA in the circuit blob.
 //
 // Stand-in for risc0-circuit-rv32im 1.2.5 `CircuitHal::accumulate(ctrl, io, data, mix, accum, steps)` (un-vendored; the circuit
 // crate's `prove/hal/{cpu,cuda}.rs`, called by `prove_segment` between the data commit and the accum commit -- in-tree call site
 // /root/reference/crates/guest-prover-r0/src/prover.rs:90).  In the reference the per-cycle accumulation step is generated code
-// of the circuit (`step_compute_accum` / `step_verify_accum`, run over every cycle with the Fiat-Shamir `mix` values, plus
-// `Hal::prefix_products` for the grand products).  The generated rv32im step functions are not obtainable offline (SURVEY.md
-// 8c), so -- exactly like eval_check -- the op is implemented for the synthetic SYN family ("SYN<W>:v1" circuit info, defined in
-// zktls_b200/circuit.py next to its constraints):
-//     even accum column j, live row i:  a_j[i] = m_{j mod M} * d_{j mod D}[i] + d_{(j+1) mod D}[i-1]
-//     odd  accum column j, live row i:  a_j[i] = a_{j-1}[i-1] * a_{j-1}[i] + m_{j mod M} + o_{j mod O}
-// where a row is live when the selector code[0][i] is one; the other rows keep what the caller put there (the reference fills
-// its trailing ZK rows with noise the same way).  One thread per row, consecutive threads on consecutive rows: every access is
-// a full 128-byte line; 4 bytes read per (row, source column), 4 written: HBM-bound.
+// of the circuit (`step_compute_accum` / `step_verify_accum`, run over every cycle with the Fiat-Shamir `mix` values) followed by
+// `Hal::prefix_products` for the grand-product columns.  Here -- exactly like eval_check's `poly_ext` -- it arrives as a step
+// program in the blob (DESIGN.md "circuit blob": Const / Get(group, column, back) / GetGlobal / Add / Sub / Mul, Set(accum column,
+// value, condition), Barrier, PrefixProduct(first of 4 accum columns)), is turned into one straight-line kernel per phase with NVRTC
+// (csrc/k_eval_jit.cu: accumulate_jit; cubins share eval_check's cache) and run one thread per row: consecutive threads on
+// consecutive rows, every access a full 128-byte line, HBM-bound.  A PrefixProduct phase gathers its four planar columns into Fp4
+// elements, runs the chunked device scan of `prefix_products` and scatters them back.  The SYN family is simply the first user
+// (its program is written next to its constraints in zktls_b200/circuit.py); nothing here knows a circuit by name.
 #include "common.cuh"
 #include "circuit.hpp"
+#include "ops.cuh"
 
 namespace zkb {
 
-struct AccumArgs { uint32_t accum_cols, data_cols, mix_size, out_size; };
+bool accumulate_jit(zkb_ctx* ctx, const CircuitDef& c, size_t phase, uint32_t* d_accum, const uint32_t* d_code, const uint32_t* d_data, const uint32_t* d_gl, uint32_t n, std::string& why);
 
-// parity = 0: even columns (functions of data only); parity = 1: odd columns (functions of the finished even columns)
-__global__ void __launch_bounds__(256) k_syn_accumulate(uint32_t* __restrict__ accum, const uint32_t* __restrict__ code, const uint32_t* __restrict__ data,
-                                                         const uint32_t* __restrict__ mix, const uint32_t* __restrict__ out_g, AccumArgs a, uint32_t n, uint32_t parity) {
+__global__ void __launch_bounds__(256) k_planar_to_fp4(uint4* __restrict__ out, const uint32_t* __restrict__ col, uint32_t n) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= n) return;
-  if (__ldg(code + i) != R_MOD_P) return;                       // selector column: Montgomery one on live rows
-  const uint32_t ip = (i + n - 1u) & (n - 1u);                  // previous row, cyclic
-  for (uint32_t j = parity; j < a.accum_cols; j += 2) {
-    const uint32_t m = __ldg(mix + j % a.mix_size);
-    uint32_t v;
-    if (parity == 0) {
-      const uint32_t d0 = __ldg(data + (size_t)(j % a.data_cols) * n + i), d1 = __ldg(data + (size_t)((j + 1) % a.data_cols) * n + ip);
-      v = add_mod(mont_mul(m, d0), d1);
-    } else {
-      const uint32_t* prev = accum + (size_t)(j - 1) * n;
-      v = add_mod(add_mod(mont_mul(prev[ip], prev[i]), m), __ldg(out_g + j % a.out_size));
-    }
-    accum[(size_t)j * n + i] = v;
-  }
+  if (i < n) out[i] = make_uint4(col[i], col[(size_t)n + i], col[2 * (size_t)n + i], col[3 * (size_t)n + i]);
 }
-
-static bool is_syn(const CircuitDef& c) { return c.info[0] == 'S' && c.info[1] == 'Y' && c.info[2] == 'N' && memchr(c.info, ':', 16) && !memcmp((const char*)memchr(c.info, ':', 16), ":v1", 3); }
+__global__ void __launch_bounds__(256) k_fp4_to_planar(uint32_t* __restrict__ col, const uint4* __restrict__ in, uint32_t n) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i < n) { const uint4 v = in[i]; col[i] = v.x; col[(size_t)n + i] = v.y; col[2 * (size_t)n + i] = v.z; col[3 * (size_t)n + i] = v.w; }
+}
 
 void accumulate(zkb_ctx* ctx, const CircuitDef& c, uint32_t* d_accum, const uint32_t* d_code, const uint32_t* d_data, const uint32_t* h_mix, const uint32_t* h_io, int po2) {
   ZKB_REQUIRE(po2 >= 1 && po2 <= 24, "accumulate: po2 out of range");
-  if (!is_syn(c)) throw Error("zkb200: accumulate: no witness program for circuit '" + std::string((const char*)c.info, 16) + "' (built in: the SYN family)");
-  ZKB_REQUIRE(c.group_size[GROUP_CODE] >= 1 && c.group_size[GROUP_DATA] >= 1 && c.mix_size >= 1 && c.out_size >= 1, "accumulate: malformed SYN circuit");
+  if (c.wsteps.empty()) throw Error("zkb200: accumulate: the circuit blob of '" + std::string((const char*)c.info, 16) + "' carries no witness program");
   if (c.group_size[GROUP_ACCUM] == 0) return;
   const uint32_t n = 1u << po2;
   uint32_t* d_gl = nullptr;
-  pool_alloc(ctx, &d_gl, (size_t)(c.mix_size + c.out_size) * 4);
-  ZKB_CUDA(cudaMemcpyAsync(d_gl, h_mix, c.mix_size * 4, cudaMemcpyHostToDevice, ctx->stream));
-  ZKB_CUDA(cudaMemcpyAsync(d_gl + c.mix_size, h_io, c.out_size * 4, cudaMemcpyHostToDevice, ctx->stream));
-  AccumArgs a{c.group_size[GROUP_ACCUM], c.group_size[GROUP_DATA], c.mix_size, c.out_size};
-  for (uint32_t parity = 0; parity < 2 && parity < a.accum_cols; ++parity) {
-    k_syn_accumulate<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_accum, d_code, d_data, d_gl, d_gl + c.mix_size, a, n, parity);
-    launched(ctx);
+  pool_alloc(ctx, &d_gl, (size_t)std::max<uint32_t>(c.mix_size + c.out_size, 4) * 4);
+  if (c.mix_size) ZKB_CUDA(cudaMemcpyAsync(d_gl, h_mix, c.mix_size * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (c.out_size) ZKB_CUDA(cudaMemcpyAsync(d_gl + c.mix_size, h_io, c.out_size * 4, cudaMemcpyHostToDevice, ctx->stream));
+  size_t phase = 0, lo = 0;
+  for (size_t i = 0; i <= c.wsteps.size(); ++i) {
+    const bool end = i == c.wsteps.size();
+    if (!end && c.wsteps[i].op != WX_BARRIER && c.wsteps[i].op != WX_PREFIX_PRODUCT) continue;
+    if (i > lo) {      // a non-empty phase
+      std::string why;
+      if (!accumulate_jit(ctx, c, phase, d_accum, d_code, d_data, d_gl, n, why)) { pool_free(ctx, d_gl); throw Error("zkb200: accumulate needs the NVRTC JIT: " + why); }
+    }
+    ++phase; lo = i + 1;
+    if (!end && c.wsteps[i].op == WX_PREFIX_PRODUCT) {
+      uint32_t* col = d_accum + (size_t)c.wsteps[i].a * n;
+      uint32_t* tmp = nullptr;
+      pool_alloc(ctx, &tmp, (size_t)n * 16);
+      k_planar_to_fp4<<<grid_for(n, 256), 256, 0, ctx->stream>>>((uint4*)tmp, col, n); launched(ctx);
+      prefix_products(ctx, tmp, n);
+      k_fp4_to_planar<<<grid_for(n, 256), 256, 0, ctx->stream>>>(col, (const uint4*)tmp, n); launched(ctx);
+      pool_free(ctx, tmp);
+    }
   }
   pool_free(ctx, d_gl);
 }
@@ -68,9 +67,10 @@ extern "C" zkb_err zkb_accumulate(zkb_ctx* ctx, const uint32_t* h_circuit, size_
                                   const uint32_t* h_mix, const uint32_t* h_io, int po2) {
   ZKB_API_BEGIN
   use(ctx);
-  ZKB_REQUIRE(h_circuit && h_mix && h_io, "null argument");
+  ZKB_REQUIRE(h_circuit, "null argument");
   CircuitDef c = CircuitDef::parse(h_circuit, circuit_words);
-  ZKB_REQUIRE((d_accum || c.group_size[GROUP_ACCUM] == 0) && d_code && d_data, "null group buffer");
+  ZKB_REQUIRE((h_mix || c.mix_size == 0) && (h_io || c.out_size == 0), "null globals");
+  ZKB_REQUIRE((d_accum || c.group_size[GROUP_ACCUM] == 0) && (d_code || c.group_size[GROUP_CODE] == 0) && (d_data || c.group_size[GROUP_DATA] == 0), "null group buffer");
   accumulate(ctx, c, (uint32_t*)d_accum, (const uint32_t*)d_code, (const uint32_t*)d_data, h_mix, h_io, po2);
   ZKB_API_END
 }

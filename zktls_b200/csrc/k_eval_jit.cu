@@ -21,6 +21,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <fcntl.h>
+#include <functional>
+#include <thread>
+#include <nvJitLink.h>
 #include <cerrno>
 #include <fstream>
 #include <sstream>
@@ -43,6 +46,20 @@ struct Api {
   decltype(&nvrtcGetProgramLog) getLog;
   decltype(&nvrtcDestroyProgram) destroyProgram;
   decltype(&nvrtcVersion) version = nullptr;
+  decltype(&nvrtcGetPTXSize) getPTXSize = nullptr;
+  decltype(&nvrtcGetPTX) getPTX = nullptr;
+  // nvJitLink (flat form of heavy circuits: NVRTC kernel PTX + hand-emitted unit PTX -> one cubin); entry points are versioned (__nvJitLinkCreate_12_x)
+  bool jl_ok = false; std::string jl_why;
+  nvJitLinkResult (*jlCreate)(nvJitLinkHandle*, uint32_t, const char**) = nullptr;
+  nvJitLinkResult (*jlDestroy)(nvJitLinkHandle*) = nullptr;
+  nvJitLinkResult (*jlAddData)(nvJitLinkHandle, nvJitLinkInputType, const void*, size_t, const char*) = nullptr;
+  nvJitLinkResult (*jlComplete)(nvJitLinkHandle) = nullptr;
+  nvJitLinkResult (*jlCubinSize)(nvJitLinkHandle, size_t*) = nullptr;
+  nvJitLinkResult (*jlCubin)(nvJitLinkHandle, void*) = nullptr;
+  nvJitLinkResult (*jlLogSize)(nvJitLinkHandle, size_t*) = nullptr;
+  nvJitLinkResult (*jlLog)(nvJitLinkHandle, char*) = nullptr;
+  nvJitLinkResult (*jlInfoSize)(nvJitLinkHandle, size_t*) = nullptr;
+  nvJitLinkResult (*jlInfo)(nvJitLinkHandle, char*) = nullptr;
   CUresult (*moduleLoadData)(CUmodule*, const void*);
   CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*);
   CUresult (*moduleUnload)(CUmodule);
@@ -70,7 +87,27 @@ Api& api() {
     a.getLog = (decltype(a.getLog))sym(rt, "nvrtcGetProgramLog");
     a.destroyProgram = (decltype(a.destroyProgram))sym(rt, "nvrtcDestroyProgram");
     a.version = (decltype(a.version))dlsym(rt, "nvrtcVersion");
+    a.getPTXSize = (decltype(a.getPTXSize))dlsym(rt, "nvrtcGetPTXSize");
+    a.getPTX = (decltype(a.getPTX))dlsym(rt, "nvrtcGetPTX");
     a.ok = all;
+    {
+      void* jl = nullptr;
+      for (const char* name : {"libnvJitLink.so.12", "libnvJitLink.so", "/usr/local/cuda/lib64/libnvJitLink.so.12"}) { jl = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (jl) break; }
+      if (!jl) a.jl_why = "libnvJitLink.so.12 not loadable";
+      else {
+        auto vsym = [&](const char* base) -> void* {
+          for (int minor = 9; minor >= 0; --minor) { std::string n = std::string("__") + base + "_12_" + std::to_string(minor); if (void* p = dlsym(jl, n.c_str())) return p; }
+          return dlsym(jl, base);
+        };
+        a.jlCreate = (decltype(a.jlCreate))vsym("nvJitLinkCreate"); a.jlDestroy = (decltype(a.jlDestroy))vsym("nvJitLinkDestroy");
+        a.jlAddData = (decltype(a.jlAddData))vsym("nvJitLinkAddData"); a.jlComplete = (decltype(a.jlComplete))vsym("nvJitLinkComplete");
+        a.jlCubinSize = (decltype(a.jlCubinSize))vsym("nvJitLinkGetLinkedCubinSize"); a.jlCubin = (decltype(a.jlCubin))vsym("nvJitLinkGetLinkedCubin");
+        a.jlLogSize = (decltype(a.jlLogSize))vsym("nvJitLinkGetErrorLogSize"); a.jlLog = (decltype(a.jlLog))vsym("nvJitLinkGetErrorLog");
+        a.jlInfoSize = (decltype(a.jlInfoSize))vsym("nvJitLinkGetInfoLogSize"); a.jlInfo = (decltype(a.jlInfo))vsym("nvJitLinkGetInfoLog");
+        a.jl_ok = a.jlCreate && a.jlDestroy && a.jlAddData && a.jlComplete && a.jlCubinSize && a.jlCubin && a.getPTXSize && a.getPTX;
+        if (!a.jl_ok) a.jl_why = "nvJitLink / nvrtcGetPTX entry points missing";
+      }
+    }
     void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
     if (!cu) { a.cu_why = "libcuda.so.1 not loadable"; return; }
     all = true;
@@ -152,13 +189,16 @@ struct EvalJitKernel {
   CUfunction fn = nullptr;
   uint32_t n_powers = 1;
   int block = 128;                // threads per CTA (one domain point per thread)
+  int points = 0;                 // domain points per CTA if != block (flat form)
   size_t smem = 0;                // dynamic shared memory per CTA
   CUdeviceptr cdata = 0;        // __constant__ zkb_cd (per-proof powers + globals) when the circuit's data fits in 64 KB
   size_t cdata_bytes = 0;
 };
+struct AccumJitKernel { CUmodule mod = nullptr; std::vector<CUfunction> phases; };
 struct EvalJitCache {
   std::map<uint64_t, EvalJitKernel> kernels;     // keyed by hash of the circuit blob content
   std::map<uint64_t, bool> failed;
+  std::map<uint64_t, AccumJitKernel> accum;      // witness programs (CircuitHal::accumulate), one kernel per phase
 };
 
 static int min_blocks();
@@ -224,6 +264,7 @@ static int sg_block() { const char* e = getenv("ZKB_EC_BLOCK"); int v = e ? atoi
 struct GenInfo {
   uint32_t n_powers = 1;
   int block = JIT_BLOCK;     // threads per CTA
+  int points = 0;            // domain points per CTA when that differs from `block` (flat form: several warp groups per point)
   size_t smem = 0;           // dynamic shared memory (staged form)
   bool staged = false;
 };
@@ -488,6 +529,225 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
   return o.str();
 }
 
+// ---- flat form: heavy circuits -------------------------------------------------------------------------------------------------
+// rv32im's generated poly_fp has ~10^4 constraints that read the same few hundred columns from everywhere in the program: a
+// streaming column ring would re-fetch every column hundreds of times, and one straight-line function of 10^5 steps keeps ~10^3 tap
+// values live (spills) and takes ptxas tens of minutes.  For such programs the constraint tree is FLATTENED:
+//     result.tot = sum over AndEqz terms of (product of the enclosing AndCond conditions) * poly_mix^(absolute power) * value
+// (AndCond(x, c, y).tot = x.tot + c * x.mul * y.tot and x.mul = poly_mix^pow(x) with pow known statically, so every term's absolute
+// power and condition list follow from one top-down walk).  Terms under the same condition list form a group: its values are
+// accumulated unreduced in four 64-bit accumulators (one IMAD.WIDE per term and component), reduced once, multiplied by the
+// condition product once.  No Fp4 x Fp4 product is left.
+//   * a CTA owns FL_POINTS (128) consecutive domain points and brings EVERY tapped column (+ halo) into shared memory with one bulk
+//     copy each (280 columns x 576 B = 161 KB): a tap is an LDS with an immediate offset wherever it is used, nothing stays live;
+//   * the groups are cut into units of <= ZKB_EC_UNIT terms, each a __noinline__ device function (bounded compile time and register
+//     pressure); FL_GROUPS (4) warp groups of 128 threads run disjoint subsets of the units on the same 128 points and add their partial
+//     sums through shared memory (16 warps per SM although only one CTA fits).
+static bool flat_wanted(const CircuitDef& c) {
+  const char* e = getenv("ZKB_EC_FORM");
+  if (e && !strcmp(e, "flat")) return true;
+  if (e && *e) return false;
+  size_t eqz = 0;
+  for (const StepDef& s : c.steps) eqz += s.op == PX_AND_EQZ;
+  return eqz >= env_u32("ZKB_EC_FLAT_MIN", 2000, 1, 1u << 30);
+}
+struct FlatTerm { uint32_t power, cl, value; };
+// The flat form is generated as a small CUDA C++ kernel (tile load, warp-group dispatch, reduction: compiled by NVRTC with -rdc) plus
+// the units as hand-emitted PTX functions, linked with nvJitLink.  Going through CUDA C++ for the units costs ~15 ms of NVVM
+// front-end / optimiser time per constraint (6 minutes for SYN-HEAVY); as PTX only ptxas runs, on code that is already the wanted
+// instruction sequence (mul.wide / mul.lo / mul.hi Montgomery products, mad.wide accumulation, min-pinned additions).
+struct FlatProgram { std::string main_cu; std::vector<std::string> unit_ptx; int threads = 512; };
+struct PtxEmit {
+  std::ostringstream body;
+  uint32_t nr = 8, nd = 4;         // %r0 = ones, %r1..%r4 = unit totals; %rd0 = sp (shared), %rd1 = pw, %rd2 = gl
+  std::string r() { return "%r" + std::to_string(nr++); }
+  std::string rd() { return "%rd" + std::to_string(nd++); }
+  std::string add(const std::string& a, const std::string& b) {
+    std::string t = r(), u = r(), o = r();
+    body << "  add.u32 " << t << ", " << a << ", " << b << "; min.u32 " << t << ", " << t << ", %r0; sub.u32 " << u << ", " << t << ", 2013265921; min.u32 " << o << ", " << t << ", " << u << ";\n";
+    return o;
+  }
+  std::string sub(const std::string& a, const std::string& b) {
+    std::string d = r(), e = r(), o = r();
+    body << "  sub.u32 " << d << ", " << a << ", " << b << "; min.u32 " << d << ", " << d << ", %r0; add.u32 " << e << ", " << d << ", 2013265921; min.u32 " << o << ", " << d << ", " << e << ";\n";
+    return o;
+  }
+  // Montgomery reduction of {lo, hi}: hi - hi(lo * P^-1 * P), canonical
+  std::string redc(const std::string& lo, const std::string& hi) {
+    std::string m = r(), u = r(), x = r(), y = r(), o = r();
+    body << "  mul.lo.u32 " << m << ", " << lo << ", 0x88000001; mul.hi.u32 " << u << ", " << m << ", 2013265921; sub.u32 " << x << ", " << hi << ", " << u << "; min.u32 " << x << ", " << x
+         << ", %r0; add.u32 " << y << ", " << x << ", 2013265921; min.u32 " << o << ", " << x << ", " << y << ";\n";
+    return o;
+  }
+  std::string mul(const std::string& a, const std::string& b) {
+    std::string t = rd(), lo = r(), hi = r();
+    body << "  mul.wide.u32 " << t << ", " << a << ", " << b << "; mov.b64 {" << lo << ", " << hi << "}, " << t << ";\n";
+    return redc(lo, hi);
+  }
+  void fixhi(const std::string& acc) {
+    std::string lo = r(), hi = r(), h2 = r();
+    body << "  mov.b64 {" << lo << ", " << hi << "}, " << acc << "; sub.u32 " << h2 << ", " << hi << ", 2013265921; min.u32 " << hi << ", " << hi << ", " << h2 << "; mov.b64 " << acc << ", {" << lo << ", " << hi << "};\n";
+  }
+  std::string fin(const std::string& acc) {
+    std::string lo = r(), hi = r(), h2 = r();
+    body << "  mov.b64 {" << lo << ", " << hi << "}, " << acc << "; sub.u32 " << h2 << ", " << hi << ", 2013265921; min.u32 " << hi << ", " << hi << ", " << h2 << ";\n";
+    return redc(lo, hi);
+  }
+};
+static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
+  const size_t n = c.steps.size();
+  std::vector<size_t> fp_step(c.n_fp_vars), mx_step(c.n_mix_vars);
+  { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) fp_step[fi++] = i; else mx_step[mi++] = i; } }
+  // static power of every mix value
+  std::vector<uint32_t> mpow(c.n_mix_vars, 0);
+  for (uint32_t m = 0; m < c.n_mix_vars; ++m) {
+    const StepDef& s = c.steps[mx_step[m]];
+    if (s.op == PX_AND_EQZ) mpow[m] = mpow[s.a] + 1; else if (s.op == PX_AND_COND) mpow[m] = mpow[s.a] + mpow[s.c];
+  }
+  // top-down walk from the result: (mix value, power offset, condition list)
+  std::vector<std::vector<uint32_t>> cls(1);                 // interned condition lists; 0 = empty
+  std::map<std::vector<uint32_t>, uint32_t> cl_id{{{}, 0u}};
+  std::vector<FlatTerm> terms;
+  struct Item { uint32_t m, off, cl; };
+  std::vector<Item> stack{{c.ret, 0u, 0u}};
+  while (!stack.empty()) {
+    Item it = stack.back(); stack.pop_back();
+    for (;;) {
+      const StepDef& s = c.steps[mx_step[it.m]];
+      if (s.op == PX_TRUE) break;
+      if (s.op == PX_AND_EQZ) { terms.push_back({it.off + mpow[s.a], it.cl, s.b}); it.m = s.a; continue; }
+      std::vector<uint32_t> inner = cls[it.cl]; inner.push_back(s.b);          // AndCond(x = s.a, cond = s.b, y = s.c)
+      auto f = cl_id.find(inner);
+      uint32_t id;
+      if (f == cl_id.end()) { id = (uint32_t)cls.size(); cl_id.emplace(inner, id); cls.push_back(inner); } else id = f->second;
+      stack.push_back({s.c, it.off + mpow[s.a], id});
+      it.m = s.a;
+    }
+  }
+  if (terms.empty()) return false;
+  std::stable_sort(terms.begin(), terms.end(), [](const FlatTerm& x, const FlatTerm& y) { return x.cl != y.cl ? x.cl < y.cl : x.power < y.power; });
+  uint32_t n_powers = 1;
+  for (const FlatTerm& t : terms) n_powers = std::max(n_powers, t.power + 1);
+  gi.n_powers = n_powers;
+  // columns: every tapped column is resident
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> slot;
+  uint32_t halo = 0;
+  for (const TapDef& t : c.taps) { slot.emplace(std::make_pair(t.group, t.column), 0u); halo = std::max(halo, 4 * t.back); }
+  { uint32_t k = 0; for (auto& kv : slot) kv.second = k++; }
+  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", 4, 1, 8);
+  uint32_t points = env_u32("ZKB_EC_FLAT_POINTS", 128, 32, 512);
+  while (points > 32 && ((size_t)slot.size() * (points + halo) * 4 + (size_t)(groups - 1) * points * 16 + 64 > 220 * 1024)) points >>= 1;
+  const uint32_t rowp = points + halo;
+  const size_t col_words = (size_t)slot.size() * rowp;
+  gi.smem = col_words * 4 + (size_t)(groups - 1) * points * 16 + 16;
+  if (gi.smem > 220 * 1024 || (halo & 3)) return false;
+  gi.block = (int)(points * groups); gi.points = (int)points; gi.staged = true;
+  // units
+  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", 256, 8, 512);
+  struct Unit { size_t lo, hi; };
+  std::vector<Unit> units;
+  for (size_t i = 0; i < terms.size();) {
+    size_t j = i;
+    while (j < terms.size() && j - i < unit_terms) {           // whole groups while they fit; a group longer than a unit is cut
+      size_t g_end = j; while (g_end < terms.size() && terms[g_end].cl == terms[j].cl) ++g_end;
+      if (g_end - i <= unit_terms || j == i) j = std::min(g_end, i + unit_terms); else break;
+    }
+    units.push_back({i, j}); i = j;
+  }
+  // ---- the units, as PTX -----------------------------------------------------------------------------------------------
+  const uint32_t per_module = env_u32("ZKB_EC_FLAT_MODULE", 16, 1, 1u << 20);      // unit functions per PTX module (one ptxas run each)
+  prog.unit_ptx.clear();
+  std::ostringstream mod;
+  auto begin_module = [&] { mod.str(std::string()); mod << ".version 8.6\n.target sm_100a\n.address_size 64\n\n"; };      // 8.6 = the first ISA with sm_100a: accepted by every nvJitLink 12.x that knows the target
+  begin_module();
+  for (size_t u = 0; u < units.size(); ++u) {
+    PtxEmit e;
+    // Get / Const / GetGlobal are loaded where they are used; arithmetic nodes become registers local to one group
+    std::function<std::string(uint32_t, std::map<uint32_t, std::string>&)> operand = [&](uint32_t f, std::map<uint32_t, std::string>& local) -> std::string {
+      auto it = local.find(f);
+      if (it != local.end()) return it->second;
+      const StepDef& s = c.steps[fp_step[f]];
+      if (s.op == PX_CONST) { std::string x = e.r(); e.body << "  mov.u32 " << x << ", " << Fp::from(s.a).v << ";\n"; return x; }
+      if (s.op == PX_GET) {
+        const TapDef& t = c.taps[s.a];
+        std::string x = e.r();
+        e.body << "  ld.shared.u32 " << x << ", [%rd0+" << 4 * ((long)slot[{t.group, t.column}] * rowp - 4 * (long)t.back) << "];\n";
+        return x;
+      }
+      if (s.op == PX_GET_GLOBAL) { std::string x = e.r(); e.body << "  ld.global.nc.u32 " << x << ", [%rd2+" << 4 * (s.a == 0 ? s.b : c.mix_size + s.b) << "];\n"; return x; }
+      std::string x = operand(s.a, local), y = operand(s.b, local);
+      std::string o = s.op == PX_ADD ? e.add(x, y) : s.op == PX_SUB ? e.sub(x, y) : e.mul(x, y);
+      local[f] = o;
+      return o;
+    };
+    for (size_t i = units[u].lo; i < units[u].hi;) {
+      size_t j = i; while (j < units[u].hi && terms[j].cl == terms[i].cl) ++j;
+      std::map<uint32_t, std::string> local;
+      std::string A[4] = {e.rd(), e.rd(), e.rd(), e.rd()};
+      for (size_t k = i; k < j; ++k) {
+        std::string v = operand(terms[k].value, local);
+        std::string w[4] = {e.r(), e.r(), e.r(), e.r()};
+        e.body << "  ld.global.nc.v4.u32 {" << w[0] << ", " << w[1] << ", " << w[2] << ", " << w[3] << "}, [%rd1+" << 16 * (size_t)terms[k].power << "];\n";
+        for (int q = 0; q < 4; ++q) {
+          if (k == i) e.body << "  mul.wide.u32 " << A[q] << ", " << v << ", " << w[q] << ";\n";
+          else e.body << "  mad.wide.u32 " << A[q] << ", " << v << ", " << w[q] << ", " << A[q] << ";\n";
+        }
+        if (((k - i) & 1) == 1 && k + 1 < j) for (int q = 0; q < 4; ++q) e.fixhi(A[q]);
+      }
+      std::string leaf[4];
+      for (int q = 0; q < 4; ++q) leaf[q] = e.fin(A[q]);
+      const std::vector<uint32_t>& cl = cls[terms[i].cl];
+      if (!cl.empty()) {
+        std::string cp = operand(cl[0], local);
+        for (size_t q = 1; q < cl.size(); ++q) cp = e.mul(cp, operand(cl[q], local));
+        for (int q = 0; q < 4; ++q) leaf[q] = e.mul(leaf[q], cp);
+      }
+      for (int q = 0; q < 4; ++q) { std::string t = e.add("%r" + std::to_string(1 + q), leaf[q]); e.body << "  mov.u32 %r" << 1 + q << ", " << t << ";\n"; }
+      i = j;
+    }
+    const std::string fn = "zkb_u" + std::to_string(u);
+    mod << ".visible .func  (.param .align 16 .b8 func_retval0[16]) " << fn << "(\n  .param .b64 " << fn << "_param_0,\n  .param .b64 " << fn << "_param_1,\n  .param .b64 "
+        << fn << "_param_2,\n  .param .b32 " << fn << "_param_3\n)\n{\n  .reg .b32 %r<" << e.nr << ">;\n  .reg .b64 %rd<" << e.nd << ">;\n"
+        << "  ld.param.u64 %rd0, [" << fn << "_param_0]; cvta.to.shared.u64 %rd0, %rd0;\n  ld.param.u64 %rd1, [" << fn << "_param_1]; cvta.to.global.u64 %rd1, %rd1;\n"
+        << "  ld.param.u64 %rd2, [" << fn << "_param_2]; cvta.to.global.u64 %rd2, %rd2;\n  ld.param.u32 %r0, [" << fn << "_param_3];\n"
+        << "  mov.u32 %r1, 0; mov.u32 %r2, 0; mov.u32 %r3, 0; mov.u32 %r4, 0;\n" << e.body.str()
+        << "  st.param.v4.b32 [func_retval0], {%r1, %r2, %r3, %r4};\n  ret;\n}\n\n";
+    if ((u + 1) % per_module == 0 || u + 1 == units.size()) { prog.unit_ptx.push_back(mod.str()); begin_module(); }
+  }
+  // ---- the kernel, as CUDA C++ ---------------------------------------------------------------------------------------------
+  std::ostringstream o;
+  o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
+  o << "#define HALO " << halo << "u\n#define BLOCK " << points << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
+  for (size_t u = 0; u < units.size(); ++u) o << "extern \"C\" __device__ uint4 zkb_u" << u << "(const u32* sp, const uint4* pw, const u32* gl, u32 ones);\n";
+  o << "#define UNIT(k) { const uint4 q = zkb_u##k(sp, pw, gl, zkb_ones); ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", 1) zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
+       "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
+       "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));\n"
+       "  extern __shared__ __align__(128) u32 zkb_sm[];\n"
+       "  u32* const part = zkb_sm + " << col_words << "u;\n"
+       "  u64* const full = reinterpret_cast<u64*>(part + " << (size_t)(groups - 1) * points * 4 << "u);\n"
+       "  const u32 c0 = blockIdx.x * BLOCK, pt = threadIdx.x % BLOCK, grp = threadIdx.x / BLOCK;\n"
+       "  if (threadIdx.x == 0) { mbar_init(full, 1u); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }\n  __syncthreads();\n"
+       "  if (threadIdx.x == 0) {\n    mbar_expect_tx(full, " << col_words * 4 << "u);\n";
+  for (auto& kv : slot) o << "    copy_col(zkb_sm + " << (size_t)kv.second * rowp << "u, g" << kv.first.first << " + (size_t)" << kv.first.second << " * dom, c0, mask, full);\n";
+  o << "  }\n  mbar_wait(full, 0u);\n  const u32* const sp = zkb_sm + pt + HALO;\n  u32 ra = 0u, rb = 0u, rc = 0u, rd = 0u;\n  switch (grp) {\n";
+  for (uint32_t g = 0; g < groups; ++g) {
+    o << "    case " << g << ":\n";
+    for (size_t u = g; u < units.size(); u += groups) o << "      UNIT(" << u << ")\n";
+    o << "      break;\n";
+  }
+  o << "  }\n";
+  if (groups > 1) o << "  if (grp) { uint4* q = reinterpret_cast<uint4*>(part) + (grp - 1u) * BLOCK + pt; *q = make_uint4(ra, rb, rc, rd); }\n  __syncthreads();\n  if (grp) return;\n"
+                       "  for (u32 g = 0; g < " << groups - 1 << "u; ++g) { const uint4 q = reinterpret_cast<const uint4*>(part)[g * BLOCK + pt]; ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
+  o << "  const u32 c = c0 + pt;\n"
+       "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n"
+       "  st(check + c, mul(ra, den)); st(check + dom + c, mul(rb, den)); st(check + 2 * dom + c, mul(rc, den)); st(check + 3 * dom + c, mul(rd, den));\n}\n";
+  prog.main_cu = o.str();
+  prog.threads = gi.block;
+  return true;
+}
+static std::string flat_text(const FlatProgram& p) { std::string t = p.main_cu; for (const std::string& u : p.unit_ptx) { t += "\n//----\n"; t += u; } return t; }
+
 // ---- on-disk cubin cache -------------------------------------------------------------------------------------------------
 // A cubin found on disk is code that will run inside the prover's CUDA context, next to the private witness, so the cache
 // follows the rules of any per-user code cache:
@@ -535,6 +795,7 @@ static uint64_t second_key(const std::string& src) {
   int maj = 0, min = 0; if (api().version) api().version(&maj, &min);
   std::string salt = "zkb200-jit-v2|nvrtc " + std::to_string(maj) + "." + std::to_string(min);
   for (const char* o : NVRTC_OPTS) { salt += '|'; salt += o; }
+  if (const char* extra = getenv("ZKB_EC_NVRTC_EXTRA")) { salt += '|'; salt += extra; }
   uint64_t h = fnv1a_bytes(salt.data(), salt.size(), 0x9e3779b97f4a7c15ull);
   return fnv1a_bytes(src.data(), src.size(), h) ^ (uint64_t)src.size();
 }
@@ -583,7 +844,10 @@ static bool compile(const std::string& src, std::vector<char>& cubin, std::strin
   }
   nvrtcProgram prog;
   if (a.createProgram(&prog, src.c_str(), "zkb_eval_check.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { why = "nvrtcCreateProgram failed"; return false; }
-  nvrtcResult r = a.compileProgram(prog, (int)(sizeof NVRTC_OPTS / sizeof NVRTC_OPTS[0]), NVRTC_OPTS);
+  std::vector<const char*> opts(NVRTC_OPTS, NVRTC_OPTS + sizeof NVRTC_OPTS / sizeof NVRTC_OPTS[0]);
+  const char* extra = getenv("ZKB_EC_NVRTC_EXTRA");      // experiments only (e.g. --ptxas-options=-O1); part of the cache key through second_key()
+  if (extra && *extra) opts.push_back(extra);
+  nvrtcResult r = a.compileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t ls = 0; a.getLogSize(prog, &ls);
     std::string log(ls, '\0'); if (ls) a.getLog(prog, &log[0]);
@@ -598,17 +862,159 @@ static bool compile(const std::string& src, std::vector<char>& cubin, std::strin
   return true;
 }
 
+// Flat form: NVRTC (-rdc) turns the kernel into PTX, nvJitLink compiles it together with the unit PTX modules into one cubin.
+static bool compile_flat(const FlatProgram& prog, std::vector<char>& cubin, std::string& why, bool ignore_disk = false) {
+  std::lock_guard<std::mutex> lock(g_compile_mutex);
+  Api& a = api();
+  if (!a.jl_ok) { why = a.jl_why.empty() ? "nvJitLink unavailable" : a.jl_why; return false; }
+  const std::string text = flat_text(prog);
+  const uint64_t key = fnv1a(text), key2 = second_key(text) ^ 0x666c6174ull;
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? std::string() : cubin_path(dir, key);
+  if (!path.empty()) {
+    if (ignore_disk) unlink(path.c_str());
+    else if (cache_read(path, key, key2, cubin)) return true;
+  }
+  nvrtcProgram np;
+  if (a.createProgram(&np, prog.main_cu.c_str(), "zkb_eval_check_flat.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { why = "nvrtcCreateProgram failed"; return false; }
+  const char* opts[] = {"--gpu-architecture=compute_100a", "--std=c++17", "-lineinfo", "--restrict", "-rdc=true"};
+  nvrtcResult r = a.compileProgram(np, 5, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t ls = 0; a.getLogSize(np, &ls);
+    std::string log(ls, '\0'); if (ls) a.getLog(np, &log[0]);
+    why = "nvrtc compile (flat kernel) failed: " + log.substr(0, 600);
+    a.destroyProgram(&np);
+    return false;
+  }
+  size_t psz = 0; a.getPTXSize(np, &psz);
+  std::string main_ptx(psz, '\0'); a.getPTX(np, &main_ptx[0]);
+  a.destroyProgram(&np);
+  // NVRTC and nvJitLink may come from different CUDA 12.x installs in one process (torch brings its own): an nvJitLink older than
+  // NVRTC rejects the newer `.version`.  The kernel uses nothing beyond ISA 8.6 (the first with sm_100a), so declare that.
+  { size_t v = main_ptx.find(".version "); if (v != std::string::npos) { size_t e = main_ptx.find('\n', v); main_ptx.replace(v, e - v, ".version 8.6"); } }
+  nvJitLinkHandle h;
+  // the units are separate functions: ptxas must be told the register budget the kernel's launch bounds imply
+  const std::string maxreg = "-maxrregcount=" + std::to_string(std::min(255, (65536 / std::max(prog.threads, 32)) & ~7));
+  // --split-compile=0: ptxas compiles the functions of a module on all host threads (2.2 x faster here with 8 threads)
+  // (no -lineinfo: it embeds the 27 MB of unit PTX in the cubin as .nv_debug_ptx_txt sections)
+  std::vector<const char*> lopts = {"-arch=sm_100a", maxreg.c_str(), "-Xptxas=--split-compile=0"};
+  const char* jl_extra = getenv("ZKB_EC_JL_EXTRA");
+  if (jl_extra && *jl_extra) lopts.push_back(jl_extra);
+  const bool verbose = getenv("ZKB_EC_VERBOSE") != nullptr;       // ptxas -v (registers, spills, stack) of every unit to stderr
+  if (verbose) { lopts.push_back("-verbose"); lopts.push_back("-Xptxas=-v"); }
+  if (a.jlCreate(&h, (uint32_t)lopts.size(), lopts.data()) != NVJITLINK_SUCCESS) { why = "nvJitLinkCreate failed"; return false; }
+  auto fail = [&](const char* what) {
+    size_t ls = 0; std::string log;
+    if (a.jlLogSize && a.jlLog && a.jlLogSize(h, &ls) == NVJITLINK_SUCCESS && ls) { log.resize(ls); a.jlLog(h, &log[0]); }
+    why = std::string("nvJitLink ") + what + " failed: " + log.substr(0, 800);
+    a.jlDestroy(&h);
+    return false;
+  };
+  if (a.jlAddData(h, NVJITLINK_INPUT_PTX, main_ptx.c_str(), main_ptx.size(), "zkb_ec_kernel") != NVJITLINK_SUCCESS) return fail("add(kernel)");
+  for (size_t i = 0; i < prog.unit_ptx.size(); ++i)
+    if (a.jlAddData(h, NVJITLINK_INPUT_PTX, prog.unit_ptx[i].c_str(), prog.unit_ptx[i].size() + 1, ("zkb_units_" + std::to_string(i)).c_str()) != NVJITLINK_SUCCESS) return fail("add(units)");
+  if (a.jlComplete(h) != NVJITLINK_SUCCESS) return fail("link");
+  if (verbose && a.jlInfoSize && a.jlInfo) {
+    size_t ls = 0;
+    if (a.jlInfoSize(h, &ls) == NVJITLINK_SUCCESS && ls) { std::string log(ls, '\0'); a.jlInfo(h, &log[0]); fprintf(stderr, "%s\n", log.c_str()); }
+  }
+  size_t sz = 0;
+  if (a.jlCubinSize(h, &sz) != NVJITLINK_SUCCESS) return fail("cubin size");
+  cubin.resize(sz);
+  if (a.jlCubin(h, cubin.data()) != NVJITLINK_SUCCESS) return fail("cubin");
+  a.jlDestroy(&h);
+  if (!path.empty()) cache_write(dir, path, key, key2, cubin);
+  return true;
+}
+
 void eval_jit_free(zkb_ctx* ctx) {
   if (!ctx->jit) return;
   EvalJitCache* cache = (EvalJitCache*)ctx->jit;
   for (auto& kv : cache->kernels) if (kv.second.mod) api().moduleUnload(kv.second.mod);
+  for (auto& kv : cache->accum) if (kv.second.mod) api().moduleUnload(kv.second.mod);
   delete cache;
   ctx->jit = nullptr;
+}
+
+// ---- CircuitHal::accumulate as data: the circuit blob's witness program, one straight-line kernel per phase --------------------
+// (the counterpart of the reference's generated step_compute_accum; PrefixProduct phases are run by the caller in between)
+struct AccumPhase { size_t lo, hi; };
+static std::vector<AccumPhase> accum_phases(const CircuitDef& c) {
+  std::vector<AccumPhase> ph;
+  size_t lo = 0;
+  for (size_t i = 0; i <= c.wsteps.size(); ++i)
+    if (i == c.wsteps.size() || c.wsteps[i].op == WX_BARRIER || c.wsteps[i].op == WX_PREFIX_PRODUCT) { ph.push_back({lo, i}); lo = i + 1; }
+  return ph;
+}
+std::string accumulate_jit_source(const CircuitDef& c) {
+  std::ostringstream o;
+  o << "#define ZKB_ALU_ADDS 1\n" << PREAMBLE;
+  const std::vector<AccumPhase> ph = accum_phases(c);
+  uint32_t val = 0;
+  for (size_t k = 0; k < ph.size(); ++k) {
+    o << "extern \"C\" __global__ void __launch_bounds__(256) zkb_acc_" << k << "(u32* __restrict__ accum, const u32* __restrict__ code, const u32* __restrict__ data, const u32* __restrict__ gl, u32 n) {\n"
+         "  const u32 i = blockIdx.x * 256u + threadIdx.x;\n  if (i >= n) return;\n";
+    for (size_t q = ph[k].lo; q < ph[k].hi; ++q) {
+      const StepDef& s = c.wsteps[q];
+      switch (s.op) {
+        case WX_CONST: o << "  const u32 w" << val++ << " = " << Fp::from(s.a).v << "u;\n"; break;
+        case WX_GET: {
+          // a phase never reads an accum column it writes (checked by the parser): plain loads for accum, the read-only path for code / data
+          std::ostringstream idx; idx << "(size_t)" << s.b << " * n + ((i - " << s.c << "u) & (n - 1u))";
+          if (s.a == GROUP_ACCUM) o << "  const u32 w" << val++ << " = accum[" << idx.str() << "];\n";
+          else o << "  const u32 w" << val++ << " = __ldg(" << (s.a == GROUP_CODE ? "code" : "data") << " + " << idx.str() << ");\n";
+          break;
+        }
+        case WX_GET_GLOBAL: o << "  const u32 w" << val++ << " = __ldg(gl + " << (s.a == 0 ? s.b : c.mix_size + s.b) << ");\n"; break;
+        case WX_ADD: o << "  const u32 w" << val++ << " = add(w" << s.a << ", w" << s.b << ");\n"; break;
+        case WX_SUB: o << "  const u32 w" << val++ << " = sub(w" << s.a << ", w" << s.b << ");\n"; break;
+        case WX_MUL: o << "  const u32 w" << val++ << " = mul(w" << s.a << ", w" << s.b << ");\n"; break;
+        case WX_SET:
+          if (s.c == WX_ALWAYS) o << "  accum[(size_t)" << s.a << " * n + i] = w" << s.b << ";\n";
+          else o << "  if (w" << s.c << " != 0u) accum[(size_t)" << s.a << " * n + i] = w" << s.b << ";\n";
+          break;
+        default: break;
+      }
+    }
+    o << "}\n";
+  }
+  return o.str();
+}
+// Launches phase `k` kernels; returns false (with why) when the JIT toolchain is unavailable.
+bool accumulate_jit(zkb_ctx* ctx, const CircuitDef& c, size_t phase, uint32_t* d_accum, const uint32_t* d_code, const uint32_t* d_data, const uint32_t* d_gl, uint32_t n, std::string& why) {
+  Api& a = api();
+  if (!a.ok) { why = a.why; return false; }
+  if (!a.cu_ok) { why = a.cu_why; return false; }
+  if (!ctx->jit) ctx->jit = new EvalJitCache();
+  EvalJitCache* cache = (EvalJitCache*)ctx->jit;
+  const std::string src = accumulate_jit_source(c);
+  const uint64_t key = fnv1a(src);
+  auto it = cache->accum.find(key);
+  if (it == cache->accum.end()) {
+    if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return false; }
+    std::vector<char> cubin;
+    if (!compile(src, cubin, why)) { cache->failed[key] = true; return false; }
+    ZKB_CUDA(cudaFree(0));
+    AccumJitKernel k;
+    CUresult r = a.moduleLoadData(&k.mod, cubin.data());
+    if (r != CUDA_SUCCESS) { cubin.clear(); if (!compile(src, cubin, why, true)) { cache->failed[key] = true; return false; } r = a.moduleLoadData(&k.mod, cubin.data()); }
+    const size_t n_ph = accum_phases(c).size();
+    for (size_t q = 0; q < n_ph && r == CUDA_SUCCESS; ++q) { CUfunction f = nullptr; r = a.moduleGetFunction(&f, k.mod, ("zkb_acc_" + std::to_string(q)).c_str()); k.phases.push_back(f); }
+    if (r != CUDA_SUCCESS) { const char* es = nullptr; a.getErrorString(r, &es); why = std::string("accumulate JIT load: ") + (es ? es : "?"); cache->failed[key] = true; return false; }
+    it = cache->accum.emplace(key, k).first;
+  }
+  ZKB_REQUIRE(phase < it->second.phases.size(), "accumulate: phase out of range");
+  void* args[] = {&d_accum, &d_code, &d_data, &d_gl, &n};
+  CUresult r = a.launchKernel(it->second.phases[phase], (n + 255u) / 256u, 1, 1, 256, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+  if (r != CUDA_SUCCESS) { const char* es = nullptr; a.getErrorString(r, &es); throw Error(std::string("zkb200: accumulate JIT launch failed: ") + (es ? es : "?")); }
+  launched(ctx);
+  return true;
 }
 
 // The generated source (for tests / inspection) -- no device needed.
 std::string eval_jit_source(const CircuitDef& c) {
   GenInfo gi;
+  if (flat_wanted(c)) { FlatProgram fp; if (generate_flat(c, gi, fp)) return flat_text(fp); }
   if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty()) return src; }
   return generate(c, gi, false);
 }
@@ -617,39 +1023,44 @@ bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
   Api& a = api();
   if (!a.ok) { why = a.why; return false; }
   std::vector<char> cubin; GenInfo gi;
+  if (!c.wsteps.empty() && !compile(accumulate_jit_source(c), cubin, why)) return false;      // the witness program's phase kernels
+  // heavy circuits: the flat form only (the straight-line forms of a 10^5-step program take ptxas tens of minutes and spill)
+  if (flat_wanted(c)) { FlatProgram fp; if (generate_flat(c, gi, fp)) return compile_flat(fp, cubin, why); }
   // every form a proof may use: the staged kernel, and the register form used for tiny domains / unaligned sub-buffers
   if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty() && !compile(src, cubin, why)) return false; }
   return compile(generate(c, gi, false), cubin, why);
 }
 
-static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool staged, std::string& why) {
+static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool staged, std::string& why, bool flat = false) {
   Api& a = api();
   if (!a.ok) { why = a.why; return nullptr; }
   if (!a.cu_ok) { why = a.cu_why; return nullptr; }
   if (!ctx->jit) ctx->jit = new EvalJitCache();
   EvalJitCache* cache = (EvalJitCache*)ctx->jit;
   GenInfo gi;
-  std::string src = generate(c, gi, staged);
-  if (src.empty()) { why = "circuit does not fit the staged form"; return nullptr; }
+  FlatProgram fprog;
+  std::string src;
+  if (flat) { if (generate_flat(c, gi, fprog)) src = flat_text(fprog); } else src = generate(c, gi, staged);
+  if (src.empty()) { why = flat ? "circuit does not fit the flat form" : "circuit does not fit the staged form"; return nullptr; }
   const uint32_t np = gi.n_powers;
   uint64_t key = fnv1a(src);
   auto it = cache->kernels.find(key);
   if (it != cache->kernels.end()) return &it->second;
   if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return nullptr; }
   std::vector<char> cubin;
-  EvalJitKernel k; k.n_powers = np; k.block = gi.block; k.smem = gi.smem;
-  if (!compile(src, cubin, why)) { cache->failed[key] = true; return nullptr; }
+  EvalJitKernel k; k.n_powers = np; k.block = gi.block; k.smem = gi.smem; k.points = gi.points ? gi.points : gi.block;
+  if (!(flat ? compile_flat(fprog, cubin, why) : compile(src, cubin, why))) { cache->failed[key] = true; return nullptr; }
   ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
   if (r != CUDA_SUCCESS) {      // a cached cubin that does not load (other driver, damaged file) is a cache miss: drop it, recompile once
     cubin.clear();
-    if (!compile(src, cubin, why, /*ignore_disk=*/true)) { cache->failed[key] = true; return nullptr; }
+    if (!(flat ? compile_flat(fprog, cubin, why, /*ignore_disk=*/true) : compile(src, cubin, why, /*ignore_disk=*/true))) { cache->failed[key] = true; return nullptr; }
     r = a.moduleLoadData(&k.mod, cubin.data());
   }
   if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
   if (r == CUDA_SUCCESS && k.smem > 48 * 1024) r = a.funcSetAttribute(k.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k.smem);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleLoadData: ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
-  if (const_mode(c, np)) {
+  if (!flat && const_mode(c, np)) {
     r = a.moduleGetGlobal(&k.cdata, &k.cdata_bytes, k.mod, "zkb_cd");
     if (r != CUDA_SUCCESS) { const char* s = nullptr; a.getErrorString(r, &s); why = std::string("cuModuleGetGlobal(zkb_cd): ") + (s ? s : "?"); cache->failed[key] = true; return nullptr; }
   }
@@ -664,7 +1075,12 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   bool aligned = ((uintptr_t)d_check & 15) == 0;
   for (int g = 0; g < 3; ++g) if ((uintptr_t)d_groups[g] & 15) aligned = false;
   const EvalJitKernel* k = nullptr;
-  if (ec_staged() && aligned && domain >= (size_t)SG_BLOCK) {       // bulk copies need 16-byte aligned columns (pool allocations are; a caller's sub-buffer view may not be)
+  if (flat_wanted(c) && aligned) {      // heavy circuit: flat form or nothing (the interpreter is the fallback, not a ten-minute compile)
+    k = get_kernel(ctx, c, false, why, true);
+    if (k && domain < (size_t)k->points) { why = "domain smaller than one flat tile"; return false; }
+    if (!k) return false;
+  }
+  if (!k && ec_staged() && aligned && domain >= (size_t)SG_BLOCK) {       // bulk copies need 16-byte aligned columns (pool allocations are; a caller's sub-buffer view may not be)
     std::string why_staged;
     k = get_kernel(ctx, c, true, why_staged);
   }
@@ -696,7 +1112,7 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   const uint4* pw = (const uint4*)d_data; const uint32_t* d_gl = d_data + 4 * (size_t)k->n_powers;
   uint32_t mask = (uint32_t)(domain - 1);
   void* args[] = {&d_check, &g0, &g1, &g2, &pw, &d_gl, &invden, &mask};
-  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / (size_t)k->block), 1, 1, (unsigned)k->block, 1, 1, (unsigned)k->smem, (CUstream)ctx->stream, args, nullptr);
+  CUresult r = api().launchKernel(k->fn, (unsigned)(domain / (size_t)(k->points ? k->points : k->block)), 1, 1, (unsigned)k->block, 1, 1, (unsigned)k->smem, (CUstream)ctx->stream, args, nullptr);
   if (r != CUDA_SUCCESS) { const char* s = nullptr; api().getErrorString(r, &s); throw Error(std::string("zkb200: eval_check JIT launch failed: ") + (s ? s : "?")); }
   launched(ctx);
   if (d_data) pool_free(ctx, d_data);

@@ -68,7 +68,8 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
         uint32_t a = reduce_2p(v[r]), b = reduce_2p(v[r | (1 << j)]);
         v[r] = min(a + b, ones);
         uint32_t d = a - b + P;
-        if (q == 0) v[r | (1 << j)] = d;
+        // w^0 = 1: level 0 always; in the round at bit 0 (lo == 0 there) also every butterfly whose in-register offset is 0
+        if (q == 0 || (p == 0 && (r & ((1 << j) - 1)) == 0)) v[r | (1 << j)] = d;
         else v[r | (1 << j)] = shoup_lazy(d, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
       }
     }
@@ -80,7 +81,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&v)[16], const int p, cons
       for (int r = 0; r < 16; ++r) {
         if (r & (1 << j)) continue;
         uint32_t a = reduce_2p(v[r]), b = v[r | (1 << j)];
-        if (q != 0) b = shoup_lazy(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
+        if (q != 0 && !(p == 0 && (r & ((1 << j) - 1)) == 0)) b = shoup_lazy(b, __ldg(twl + (1u << q) + ((uint32_t)(r & ((1 << j) - 1)) << p) + lo));
         b = reduce_2p(b);
         v[r] = min(a + b, ones);
         v[r | (1 << j)] = a - b + P;
@@ -235,7 +236,9 @@ template <int A, int TL = 0> struct STile {
 // (ttab[l * S + p2] = mult * B^(rev_A(l)) * w_M^(+-rev_A(l) * p2)): one LDG.64 + 3 multiplier-pipe instructions per element,
 // against ~2.2 Montgomery multiplications per element for the running-product form.  The table (8 M bytes, <= 32 MB) is
 // shared by all columns and stays in L2.
-template <int A, bool INV, int TL = 0, bool TAB = false>
+// SL: log2 S as a compile-time constant (0 = take it from args): every global access of the tile is then base + immediate
+// (the 32 loads / stores of a thread cost ~80 address instructions otherwise -- 7 % of the kernel's issue slots).
+template <int A, bool INV, int TL = 0, bool TAB = false, int SL = 0>
 __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint2* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args,
                                                                  const uint2* __restrict__ ttab, const uint32_t* __restrict__ src, uint32_t ones) {
   constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
@@ -245,10 +248,10 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   const uint32_t tile = blockIdx.x & ((1u << args.tiles_per_block_log) - 1u);
   const size_t block = blockIdx.x >> args.tiles_per_block_log;
   const uint32_t p2 = (tile << T_LOG) + c2;                                 // position inside the row of S
-  const int m_log = A + (int)args.s_log;
+  const uint32_t s_log = SL ? (uint32_t)SL : args.s_log;
+  const int m_log = A + (int)s_log;
   uint32_t* const cb = io + (block << m_log);            // CTA-uniform; everything below is a 32-bit offset (< 2^26 elements)
   const uint32_t* const cin = src ? src + (block << m_log) : cb;      // inverse pass: optional separate input (the caller's trace), saving a copy
-  const uint32_t s_log = args.s_log;
   const uint32_t off_r = (t << s_log) + p2;                // element (r * TPB + t, p2): off_r + r * (TPB << s_log)
   const uint32_t off_c = ((16u * t) << s_log) + p2;        // element (16 t + r, p2):   off_c + (r << s_log)
   const uint32_t S = 1u << s_log;
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
     if (TAB) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        uint32_t x = shoup_lazy(v[r], __ldg(ttab + (off_c + ((uint32_t)r << s_log))));
+        uint32_t x = shoup_lazy(v[r], __ldg(ttab + off_c + ((size_t)r << s_log)));
         v[r] = inverse ? reduce_2p(x) : x;          // forward: the butterflies take lazy values; inverse: stored next
       }
       return;
@@ -285,7 +288,9 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   if (INV) {
     constexpr int P0 = A - 4;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = cin[off_r + (((uint32_t)r * TPB) << s_log)];
+    { const uint32_t* const pr = cin + off_r;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = pr[(size_t)((uint32_t)r * TPB) << s_log]; }
     radix_round<true, 0, 4>(v, P0, t, twl, ones);
     int p_prev = P0;
 #pragma unroll
@@ -303,12 +308,14 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
       p_prev = pc;
     }
     twiddle_all(true);
+    { uint32_t* const pc = cb + off_c;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) cb[off_c + ((uint32_t)r << s_log)] = v[r];
+      for (int r = 0; r < 16; ++r) pc[(size_t)r << s_log] = v[r]; }
   } else {
     constexpr int PLAST = A - 4;
+    { const uint32_t* const pc = cb + off_c;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = cb[off_c + ((uint32_t)r << s_log)];
+      for (int r = 0; r < 16; ++r) v[r] = pc[(size_t)r << s_log]; }
     twiddle_all(false);
     radix_round<false, 0, 4>(v, 0, 0u, twl, ones);
     int p_prev = 0;
@@ -327,8 +334,9 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
       p_prev = pc;
     }
     canonicalize(v);
+    { uint32_t* const pr = cb + off_r;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) cb[off_r + (((uint32_t)r * TPB) << s_log)] = v[r];
+      for (int r = 0; r < 16; ++r) pr[(size_t)((uint32_t)r * TPB) << s_log] = v[r]; }
   }
 }
 
@@ -429,7 +437,7 @@ static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, 
   SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
   size_t tile_elems = (size_t)(1 << A) * ST::T;
   size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
-  auto kern = ttab ? k_ntt_s<A, INV, TL, true> : k_ntt_s<A, INV, TL, false>;
+  auto kern = s_log == 12 ? (ttab ? k_ntt_s<A, INV, TL, true, 12> : k_ntt_s<A, INV, TL, false, 12>) : (ttab ? k_ntt_s<A, INV, TL, true> : k_ntt_s<A, INV, TL, false>);
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab, src, ntt_ones());
   launched(ctx);

@@ -6,6 +6,7 @@
 // every global load is a fully coalesced 128-byte line.
 #include "common.cuh"
 #include "poseidon2.cuh"
+#include "poseidon2_warp.cuh"
 
 namespace zkb {
 
@@ -51,18 +52,28 @@ __global__ void __launch_bounds__(HASH_BLOCK) k_hash_fold(uint32_t* __restrict__
   o[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
 
-// Top of the tree in one CTA: levels with <= TAIL_LEAVES/2 outputs, synchronised with __syncthreads.
-constexpr int TAIL_THREADS = 256;
-__global__ void __launch_bounds__(TAIL_THREADS) k_merkle_tail(uint32_t* __restrict__ nodes, uint32_t top_inputs, uint32_t ones) {
+// ---- top of the tree: warp-cooperative permutations (poseidon2_warp.cuh) -----------------------------------------------------
+// One warp per parent digest: lanes 0..15 load the two children (64 contiguous bytes), lanes 0..7 store the parent.
+constexpr int COOP_WARPS = 8;                       // warps per CTA
+constexpr size_t COOP_MAX_OUTPUTS = 4096;           // levels with at most this many parents use the cooperative kernels
+constexpr uint32_t COOP_TAIL_INPUTS = 64;           // the last levels (<= 32 parents) run inside one 32-warp CTA
+__global__ void __launch_bounds__(COOP_WARPS * 32) k_hash_fold_coop(uint32_t* __restrict__ nodes, size_t in_base, size_t out_base, uint32_t count) {
+  p2w::Lane L; L.init();
+  const uint32_t i = blockIdx.x * COOP_WARPS + (threadIdx.x >> 5);
+  if (i >= count) return;                           // whole warps leave together
+  uint32_t s = L.lane < 16u ? nodes[(in_base + 2 * (size_t)i) * 8 + L.lane] : 0u;
+  s = p2w::permute(L, s);
+  if (L.lane < 8u) nodes[(out_base + i) * 8 + L.lane] = s;
+}
+// levels top_inputs -> top_inputs / 2 -> ... -> 1 in one CTA of 32 warps (top_inputs <= 64)
+__global__ void __launch_bounds__(1024) k_merkle_tail_coop(uint32_t* __restrict__ nodes, uint32_t top_inputs) {
+  p2w::Lane L; L.init();
+  const uint32_t w = threadIdx.x >> 5;
   for (uint32_t outs = top_inputs >> 1; outs >= 1; outs >>= 1) {
-    for (uint32_t i = threadIdx.x; i < outs; i += TAIL_THREADS) {
-      const uint4* in = reinterpret_cast<const uint4*>(nodes + ((size_t)2 * outs + 2 * i) * 8);
-      uint4 a0 = in[0], a1 = in[1], b0 = in[2], b1 = in[3];
-      uint32_t s[24] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, 0, 0, 0, 0, 0, 0, 0, 0};
-      p2::permute(s, ZKB_P2_TABLES, ones);
-      uint4* o = reinterpret_cast<uint4*>(nodes + ((size_t)outs + i) * 8);
-      o[0] = make_uint4(s[0], s[1], s[2], s[3]);
-      o[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    if (w < outs) {
+      uint32_t s = L.lane < 16u ? nodes[((size_t)2 * outs + 2 * w) * 8 + L.lane] : 0u;
+      s = p2w::permute(L, s);
+      if (L.lane < 8u) nodes[((size_t)outs + w) * 8 + L.lane] = s;
     }
     __syncthreads();
   }
@@ -77,20 +88,28 @@ void hash_rows(zkb_ctx* ctx, uint32_t* out, const uint32_t* matrix, size_t rows,
   else k_hash_rows<256><<<grid_for(rows, 256), 256, 0, ctx->stream>>>(out, matrix, rows, (uint32_t)cols, p2_ones());
   launched(ctx);
 }
+// Levels with more than COOP_MAX_OUTPUTS parents: one thread per permutation (throughput-bound, k_hash_fold).  Below that the
+// tree is latency-bound -- fewer permutations than warps -- and every level is one launch of the warp-cooperative kernel
+// (~2.3 us of dependent work per level instead of ~19 us); the last six levels share one CTA.  Round 1 ran the levels below 2048
+// inputs in a single 256-thread CTA: eleven dependent levels at ~19 us each, 0.2 ms per tree that only other in-flight segments hid.
 void hash_fold(zkb_ctx* ctx, uint32_t* nodes, size_t input_size, size_t output_size) {
   if (output_size == 0) return;
-  k_hash_fold<<<grid_for(output_size, HASH_BLOCK), HASH_BLOCK, 0, ctx->stream>>>(nodes, input_size, output_size, output_size, p2_ones());
+  static const bool coop = [] { const char* e = getenv("ZKB_MERKLE_COOP"); return !e || atoi(e) != 0; }();
+  if (coop && output_size <= COOP_MAX_OUTPUTS) {
+    k_hash_fold_coop<<<(unsigned)((output_size + COOP_WARPS - 1) / COOP_WARPS), COOP_WARPS * 32, 0, ctx->stream>>>(nodes, input_size, output_size, (uint32_t)output_size);
+  } else {
+    k_hash_fold<<<grid_for(output_size, HASH_BLOCK), HASH_BLOCK, 0, ctx->stream>>>(nodes, input_size, output_size, output_size, p2_ones());
+  }
   launched(ctx);
 }
 void merkle_build(zkb_ctx* ctx, uint32_t* nodes, size_t rows) {
-  const size_t TAIL_INPUTS = 2048;     // levels whose input has <= 2048 digests run inside one CTA
   size_t in = rows;
-  while (in > TAIL_INPUTS) {
+  while (in > COOP_TAIL_INPUTS) {
     hash_fold(ctx, nodes, in, in / 2);
     in /= 2;
   }
   if (in >= 2) {
-    k_merkle_tail<<<1, TAIL_THREADS, 0, ctx->stream>>>(nodes, (uint32_t)in, p2_ones());
+    k_merkle_tail_coop<<<1, 1024, 0, ctx->stream>>>(nodes, (uint32_t)in);
     launched(ctx);
   }
 }
