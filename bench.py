@@ -485,7 +485,7 @@ def main():
             hal.eval_check(chk, blob, *bufs_ec, gl_m, gl_o, pm, po2)
         ms_ec = hal.timer_stop() / 3
         n_eqz = int((blob[16 + 3 * int(blob[6]):].reshape(-1, 4)[:, 0] == circuit.OP_AND_EQZ).sum())
-        ec = {"kernel": "zkb_ec (flat form: all tapped columns resident per 128-point tile, PTX units)", "ms": ms_ec, "constraints": n_eqz, "steps": int(blob[7]),
+        ec = {"kernel": "zkb_ec (compact form: all tapped columns resident per 128-point tile, one loop body per expression shape, terms as operand records)", "ms": ms_ec, "constraints": n_eqz, "steps": int(blob[7]),
               "domain_points": dom, "constraint_evaluations_per_s": n_eqz * dom / (ms_ec * 1e-3),
               "multiplier_slots_per_point": n_eqz * (4 * 2 + 5), "note": "per constraint: 4 IMAD.WIDE accumulations (8 slots) + ~1 Montgomery product (5 slots) on the multiplier pipe"}
         del bufs_ec, chk

@@ -1,7 +1,10 @@
 """eval_check on circuits with the SHAPE of rv32im's generated poly_fp (SYN-HEAVY: > 20 k constraints, > 10^5 PolyExtSteps, AndCond
-nested four deep, taps back 0..4, five combos; zktls_b200/circuit.py) -- the flat form of the JIT (all tapped columns resident in
-shared memory, constraint tree flattened into (condition product) x poly_mix^k x value terms, units emitted as PTX and linked with
-nvJitLink; csrc/k_eval_jit.cu) against the CPU oracle.  VERDICT r1 next #5."""
+nested four deep, taps back 0..4, five combos; zktls_b200/circuit.py) against the CPU oracle, in the two heavy-circuit forms of the JIT
+(csrc/k_eval_jit.cu; both keep all tapped columns resident in shared memory and flatten the constraint tree into
+(condition product) x poly_mix^k x value terms):
+  compact  the program as DATA: one loop body per distinct expression shape, terms = operand records staged in shared memory (default)
+  flat     every term as straight-line PTX, units linked with nvJitLink (fallback for circuits the compact form does not cover)
+VERDICT r1 next #5."""
 import numpy as np
 import pytest
 
@@ -47,6 +50,14 @@ def test_flat_source_is_ptx_units_plus_a_resident_tile_kernel(monkeypatch, tmp_p
     src = out.value.decode()
     assert ".visible .func" in src and "mad.wide.u32" in src and "ld.shared.u32" in src          # units: PTX
     assert "extern \"C\" __device__ uint4 zkb_u0" in src and "copy_col(" in src and "switch (grp)" in src      # kernel: tile load + warp groups
+    monkeypatch.setenv("ZKB_EC_FORM", "compact")
+    check(lib().zkb_eval_check_source(bp, C.c_size_t(blob.size), None, C.c_size_t(0), C.byref(need)))
+    out2 = C.create_string_buffer(need.value + 1)
+    check(lib().zkb_eval_check_source(bp, C.c_size_t(blob.size), out2, C.c_size_t(need.value + 1), C.byref(need)))
+    csrc = out2.value.decode()
+    assert "zkb_prog[" in csrc and "switch (shape)" in csrc and csrc.count("case ") <= 8 and ".visible .func" not in csrc      # a handful of shapes, no per-term code
+    check(lib().zkb_eval_check_precompile(bp, C.c_size_t(blob.size)))
+    monkeypatch.setenv("ZKB_EC_FORM", "flat")
     try:
         check(lib().zkb_eval_check_precompile(bp, C.c_size_t(blob.size)))
     except ZkbError as e:
@@ -77,9 +88,11 @@ def _eval_both(hal, oracle, b, po2, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("po2,env", [(5, {}), (6, {}), (8, {}), (8, {"ZKB_EC_FLAT_GROUPS": "1"}), (8, {"ZKB_EC_FLAT_GROUPS": "3", "ZKB_EC_UNIT": "16"}), (9, {"ZKB_EC_FLAT_POINTS": "64"})])
-def test_flat_form_matches_oracle_on_a_reduced_heavy_circuit(hal, oracle, po2, env, monkeypatch):
-    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+@pytest.mark.parametrize("form", ["compact", "flat"])
+@pytest.mark.parametrize("po2,env", [(5, {}), (6, {}), (8, {}), (8, {"ZKB_EC_FLAT_GROUPS": "1"}), (8, {"ZKB_EC_FLAT_GROUPS": "3", "ZKB_EC_UNIT": "16", "ZKB_EC_UNIT_VECS": "64"}),
+                                     (9, {"ZKB_EC_FLAT_POINTS": "64"})])
+def test_flat_form_matches_oracle_on_a_reduced_heavy_circuit(hal, oracle, po2, env, form, monkeypatch):
+    monkeypatch.setenv("ZKB_EC_FORM", form)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     got, want = _eval_both(hal, oracle, circuit.syn_heavy_circuit(**REDUCED), po2, 500 + po2)
@@ -87,18 +100,21 @@ def test_flat_form_matches_oracle_on_a_reduced_heavy_circuit(hal, oracle, po2, e
 
 
 @pytest.mark.gpu
-def test_flat_form_agrees_with_the_other_forms_on_syn280(hal, oracle, monkeypatch):
-    """the benchmark circuit through the flat form (it normally takes the staged form): same check polynomial"""
-    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+@pytest.mark.parametrize("form", ["compact", "flat"])
+def test_flat_form_agrees_with_the_other_forms_on_syn280(hal, oracle, form, monkeypatch):
+    """the benchmark circuit through the heavy-circuit forms (it normally takes the staged form): same check polynomial"""
+    monkeypatch.setenv("ZKB_EC_FORM", form)
     got, want = _eval_both(hal, oracle, circuit.syn_circuit(**circuit.SYN280), 7, 77)
     assert np.array_equal(got, want)
 
 
 @pytest.mark.gpu
 @pytest.mark.slow
-@pytest.mark.parametrize("po2", [8, 12])
-def test_syn_heavy_matches_oracle(hal, oracle, po2):
-    """the full SYN-HEAVY circuit (22 k constraints, 117 k steps) at po2 8 and 12: 2^10 and 2^14 domain points x 117 k steps on the oracle"""
+@pytest.mark.parametrize("po2,form", [(8, "compact"), (12, "compact"), (8, "flat")])
+def test_syn_heavy_matches_oracle(hal, oracle, po2, form, monkeypatch):
+    """the full SYN-HEAVY circuit (20.5 k constraints, 117 k steps) at po2 8 and 12: 2^10 and 2^14 domain points x 117 k steps on the
+    oracle (the PTX flat form once: its cubin takes ~30 s of ptxas when it is not in the cache)"""
+    monkeypatch.setenv("ZKB_EC_FORM", form)
     got, want = _eval_both(hal, oracle, circuit.syn_heavy_circuit(), po2, 900 + po2)
     assert np.array_equal(got, want)
 
@@ -107,7 +123,7 @@ def test_syn_heavy_matches_oracle(hal, oracle, po2):
 def test_segment_seal_with_a_heavy_circuit_matches_oracle(hal, oracle, monkeypatch):
     """whole prover with a flat-form eval_check and five combos (register sizes 1, 2, 3, 5: poly_interpolate beyond the linear case)"""
     from zktls_b200.prover import SegmentProver
-    monkeypatch.setenv("ZKB_EC_FORM", "flat")
+    monkeypatch.setenv("ZKB_EC_FORM", "compact")
     b = circuit.syn_heavy_circuit(**REDUCED)
     blob = b.blob()
     shape = dict(accum_cols=6, code_cols=6, data_cols=12, out_size=4)

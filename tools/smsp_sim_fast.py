@@ -1,9 +1,17 @@
 """Front end for the compiled issue simulator (see tools/smsp_sim.py for the model): parses SASS from stdin, flattens the loops,
-feeds /tmp/w/sim (g++ -O2 of the loop in tools/smsp_sim.py; built by tools/build_sim.sh)."""
+feeds tools/smsp_sim_core (g++ -O2 of tools/smsp_sim_core.cpp, the loop of tools/smsp_sim.py; built on first use)."""
 import subprocess, sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import smsp_sim as S
-def run(sass_text, warps=12, policy="gto", trips=(4, 21, 4), reps=3, sim="/tmp/w/sim"):
+_HERE = os.path.dirname(os.path.abspath(__file__))
+def _sim_binary():
+    exe = os.path.join(_HERE, "smsp_sim_core")
+    src = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.run(["g++", "-O2", "-o", exe, src], check=True)
+    return exe
+def run(sass_text, warps=12, policy="gto", trips=(4, 21, 4), reps=3, sim=None):
+    sim = sim or _sim_binary()
     ins = S.parse(sass_text.splitlines(True))
     seq, per = S.build_program(ins, list(trips), reps)
     pid = {"F": 0, "A": 1, "U": 2, "X": 3}

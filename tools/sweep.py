@@ -10,7 +10,7 @@ import numpy as np
 from zktls_b200.hal import B200Hal
 
 HBM = 6650.0          # GB/s, fallback peak (B200_PROFILING.md) unless MEASURED_PEAKS.json exists
-MODMUL = 3.27e12      # measured INT32 Montgomery-modmul ceiling (profiles/r1_ubench_fp64_mix.txt)
+MODMUL = 18.61e12 / 5     # Montgomery products per second at the hardware multiplier-pipe slot peak (64 lanes x 148 SMs x 1.965 GHz, 5 slots each)
 ap = argparse.ArgumentParser(); ap.add_argument("--max-po2", type=int, default=24); ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--max-bytes", type=float, default=60e9)
 a = ap.parse_args()

@@ -190,6 +190,7 @@ struct EvalJitKernel {
   uint32_t n_powers = 1;
   int block = 128;                // threads per CTA (one domain point per thread)
   int points = 0;                 // domain points per CTA if != block (flat form)
+  std::vector<uint32_t> term_power;    // flat form: the power table is laid out in term order
   size_t smem = 0;                // dynamic shared memory per CTA
   CUdeviceptr cdata = 0;        // __constant__ zkb_cd (per-proof powers + globals) when the circuit's data fits in 64 KB
   size_t cdata_bytes = 0;
@@ -265,6 +266,7 @@ struct GenInfo {
   uint32_t n_powers = 1;
   int block = JIT_BLOCK;     // threads per CTA
   int points = 0;            // domain points per CTA when that differs from `block` (flat form: several warp groups per point)
+  std::vector<uint32_t> term_power;   // flat form: entry t of the kernel's power table is poly_mix^term_power[t] (table in TERM order)
   size_t smem = 0;           // dynamic shared memory (staged form)
   bool staged = false;
 };
@@ -545,7 +547,7 @@ static std::string generate(const CircuitDef& c, GenInfo& gi, bool staged) {
 //     sums through shared memory (16 warps per SM although only one CTA fits).
 static bool flat_wanted(const CircuitDef& c) {
   const char* e = getenv("ZKB_EC_FORM");
-  if (e && !strcmp(e, "flat")) return true;
+  if (e && (!strcmp(e, "flat") || !strcmp(e, "compact"))) return true;      // forced: "compact" = program as data, "flat" = PTX units
   if (e && *e) return false;
   size_t eqz = 0;
   for (const StepDef& s : c.steps) eqz += s.op == PX_AND_EQZ;
@@ -559,7 +561,7 @@ struct FlatTerm { uint32_t power, cl, value; };
 struct FlatProgram { std::string main_cu; std::vector<std::string> unit_ptx; int threads = 512; };
 struct PtxEmit {
   std::ostringstream body;
-  uint32_t nr = 8, nd = 4;         // %r0 = ones, %r1..%r4 = unit totals; %rd0 = sp (shared), %rd1 = pw, %rd2 = gl
+  uint32_t nr = 8, nd = 4;         // %r0 = ones, %r1..%r4 = unit totals, %r5 = the warp group's named barrier; %rd0 = sp (shared), %rd1 = pw, %rd2 = gl
   std::string r() { return "%r" + std::to_string(nr++); }
   std::string rd() { return "%rd" + std::to_string(nd++); }
   std::string add(const std::string& a, const std::string& b) {
@@ -626,24 +628,29 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
   }
   if (terms.empty()) return false;
   std::stable_sort(terms.begin(), terms.end(), [](const FlatTerm& x, const FlatTerm& y) { return x.cl != y.cl ? x.cl < y.cl : x.power < y.power; });
-  uint32_t n_powers = 1;
-  for (const FlatTerm& t : terms) n_powers = std::max(n_powers, t.power + 1);
-  gi.n_powers = n_powers;
+  // the kernel's power table is laid out in TERM order (entry t = poly_mix^terms[t].power), so that a unit's slice is contiguous
+  // and can be staged in shared memory (below)
+  gi.n_powers = (uint32_t)terms.size();
+  gi.term_power.resize(terms.size());
+  for (size_t t = 0; t < terms.size(); ++t) gi.term_power[t] = terms[t].power;
   // columns: every tapped column is resident
   std::map<std::pair<uint32_t, uint32_t>, uint32_t> slot;
   uint32_t halo = 0;
   for (const TapDef& t : c.taps) { slot.emplace(std::make_pair(t.group, t.column), 0u); halo = std::max(halo, 4 * t.back); }
   { uint32_t k = 0; for (auto& kv : slot) kv.second = k++; }
   const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", 4, 1, 8);
+  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", 256, 8, 512);
+  // per warp group: the poly_mix powers of the unit it is running, staged in shared memory (one coalesced copy per unit instead of
+  // one L2-latency load per term: the L1 holds the 161 KB tile, not the 330 KB table)
+  const size_t pw_words = (size_t)groups * unit_terms * 4;
   uint32_t points = env_u32("ZKB_EC_FLAT_POINTS", 128, 32, 512);
-  while (points > 32 && ((size_t)slot.size() * (points + halo) * 4 + (size_t)(groups - 1) * points * 16 + 64 > 220 * 1024)) points >>= 1;
+  while (points > 32 && ((size_t)slot.size() * (points + halo) * 4 + (size_t)(groups - 1) * points * 16 + pw_words * 4 + 64 > 220 * 1024)) points >>= 1;
   const uint32_t rowp = points + halo;
   const size_t col_words = (size_t)slot.size() * rowp;
-  gi.smem = col_words * 4 + (size_t)(groups - 1) * points * 16 + 16;
+  gi.smem = col_words * 4 + (size_t)(groups - 1) * points * 16 + pw_words * 4 + 16;
   if (gi.smem > 220 * 1024 || (halo & 3)) return false;
   gi.block = (int)(points * groups); gi.points = (int)points; gi.staged = true;
   // units
-  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", 256, 8, 512);
   struct Unit { size_t lo, hi; };
   std::vector<Unit> units;
   for (size_t i = 0; i < terms.size();) {
@@ -656,6 +663,11 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
   }
   // ---- the units, as PTX -----------------------------------------------------------------------------------------------
   const uint32_t per_module = env_u32("ZKB_EC_FLAT_MODULE", 16, 1, 1u << 20);      // unit functions per PTX module (one ptxas run each)
+  // The code of a heavy circuit (9 MB for SYN-HEAVY) streams through the instruction caches once per tile; ncu shows the kernel bound by
+  // instruction fetch from L2 (1.14 instructions / clock / SM, 9 of 14 cycles per issued instruction "no instruction") when every warp
+  // fetches its own copy.  A named barrier every `sync_terms` terms keeps the four warps of a group within a few KB of each other, so a
+  // line fetched into the SM's 32 KB L1.5 instruction cache serves all of them.
+  const uint32_t sync_terms = env_u32("ZKB_EC_FLAT_SYNC", 16, 0, 1u << 20);
   prog.unit_ptx.clear();
   std::ostringstream mod;
   auto begin_module = [&] { mod.str(std::string()); mod << ".version 8.6\n.target sm_100a\n.address_size 64\n\n"; };      // 8.6 = the first ISA with sm_100a: accepted by every nvJitLink 12.x that knows the target
@@ -687,12 +699,13 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
       for (size_t k = i; k < j; ++k) {
         std::string v = operand(terms[k].value, local);
         std::string w[4] = {e.r(), e.r(), e.r(), e.r()};
-        e.body << "  ld.global.nc.v4.u32 {" << w[0] << ", " << w[1] << ", " << w[2] << ", " << w[3] << "}, [%rd1+" << 16 * (size_t)terms[k].power << "];\n";
+        e.body << "  ld.shared.v4.u32 {" << w[0] << ", " << w[1] << ", " << w[2] << ", " << w[3] << "}, [%r6+" << 16 * (k - units[u].lo) << "];\n";
         for (int q = 0; q < 4; ++q) {
           if (k == i) e.body << "  mul.wide.u32 " << A[q] << ", " << v << ", " << w[q] << ";\n";
           else e.body << "  mad.wide.u32 " << A[q] << ", " << v << ", " << w[q] << ", " << A[q] << ";\n";
         }
         if (((k - i) & 1) == 1 && k + 1 < j) for (int q = 0; q < 4; ++q) e.fixhi(A[q]);
+        if (sync_terms && groups > 0 && (k - units[u].lo) % sync_terms == sync_terms - 1) e.body << "  bar.sync %r5, " << points << ";\n";
       }
       std::string leaf[4];
       for (int q = 0; q < 4; ++q) leaf[q] = e.fin(A[q]);
@@ -706,11 +719,24 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
       i = j;
     }
     const std::string fn = "zkb_u" + std::to_string(u);
+    // prologue: the group's threads copy this unit's slice of the (term-ordered) power table into the group's staging area
+    std::ostringstream stage;
+    {
+      const size_t nt = units[u].hi - units[u].lo;
+      stage << "  {\n  .reg .pred %pz;\n  .reg .b32 %zi, %za, %zw<4>;\n  .reg .b64 %zg;\n  bar.sync %r5, " << points << ";\n";       // everybody is done with the previous unit's slice
+      for (size_t base = 0; base < nt; base += points) {
+        stage << "  add.u32 %zi, %r7, " << base << ";\n  setp.lt.u32 %pz, %zi, " << nt << ";\n  mul.wide.u32 %zg, %zi, 16;\n  add.u64 %zg, %zg, %rd1;\n"
+              << "  @%pz ld.global.nc.v4.u32 {%zw0, %zw1, %zw2, %zw3}, [%zg+" << 16 * units[u].lo << "];\n  shl.b32 %za, %zi, 4;\n  add.u32 %za, %za, %r6;\n"
+              << "  @%pz st.shared.v4.u32 [%za], {%zw0, %zw1, %zw2, %zw3};\n";
+      }
+      stage << "  bar.sync %r5, " << points << ";\n  }\n";
+    }
     mod << ".visible .func  (.param .align 16 .b8 func_retval0[16]) " << fn << "(\n  .param .b64 " << fn << "_param_0,\n  .param .b64 " << fn << "_param_1,\n  .param .b64 "
-        << fn << "_param_2,\n  .param .b32 " << fn << "_param_3\n)\n{\n  .reg .b32 %r<" << e.nr << ">;\n  .reg .b64 %rd<" << e.nd << ">;\n"
+        << fn << "_param_2,\n  .param .b32 " << fn << "_param_3,\n  .param .b32 " << fn << "_param_4,\n  .param .b32 " << fn << "_param_5,\n  .param .b32 " << fn << "_param_6\n)\n{\n  .reg .b32 %r<" << e.nr << ">;\n  .reg .b64 %rd<" << e.nd << ">;\n"
         << "  ld.param.u64 %rd0, [" << fn << "_param_0]; cvta.to.shared.u64 %rd0, %rd0;\n  ld.param.u64 %rd1, [" << fn << "_param_1]; cvta.to.global.u64 %rd1, %rd1;\n"
-        << "  ld.param.u64 %rd2, [" << fn << "_param_2]; cvta.to.global.u64 %rd2, %rd2;\n  ld.param.u32 %r0, [" << fn << "_param_3];\n"
-        << "  mov.u32 %r1, 0; mov.u32 %r2, 0; mov.u32 %r3, 0; mov.u32 %r4, 0;\n" << e.body.str()
+        << "  ld.param.u64 %rd2, [" << fn << "_param_2]; cvta.to.global.u64 %rd2, %rd2;\n  ld.param.u32 %r0, [" << fn << "_param_3];\n  ld.param.u32 %r5, [" << fn << "_param_4];\n"
+        << "  ld.param.u32 %r6, [" << fn << "_param_5];\n  ld.param.u32 %r7, [" << fn << "_param_6];\n"
+        << "  mov.u32 %r1, 0; mov.u32 %r2, 0; mov.u32 %r3, 0; mov.u32 %r4, 0;\n" << stage.str() << e.body.str()
         << "  st.param.v4.b32 [func_retval0], {%r1, %r2, %r3, %r4};\n  ret;\n}\n\n";
     if ((u + 1) % per_module == 0 || u + 1 == units.size()) { prog.unit_ptx.push_back(mod.str()); begin_module(); }
   }
@@ -718,15 +744,17 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
   std::ostringstream o;
   o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
   o << "#define HALO " << halo << "u\n#define BLOCK " << points << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
-  for (size_t u = 0; u < units.size(); ++u) o << "extern \"C\" __device__ uint4 zkb_u" << u << "(const u32* sp, const uint4* pw, const u32* gl, u32 ones);\n";
-  o << "#define UNIT(k) { const uint4 q = zkb_u##k(sp, pw, gl, zkb_ones); ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
+  for (size_t u = 0; u < units.size(); ++u) o << "extern \"C\" __device__ uint4 zkb_u" << u << "(const u32* sp, const uint4* pw, const u32* gl, u32 ones, u32 bar, u32 pwsm, u32 pt);\n";
+  o << "#define UNIT(k) { const uint4 q = zkb_u##k(sp, pw, gl, zkb_ones, grp + 1u, pwsm, pt); ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
   o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", 1) zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
        "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
        "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));\n"
        "  extern __shared__ __align__(128) u32 zkb_sm[];\n"
        "  u32* const part = zkb_sm + " << col_words << "u;\n"
-       "  u64* const full = reinterpret_cast<u64*>(part + " << (size_t)(groups - 1) * points * 4 << "u);\n"
+       "  u32* const pwst = part + " << (size_t)(groups - 1) * points * 4 << "u;          // per warp group: the running unit's poly_mix powers\n"
+       "  u64* const full = reinterpret_cast<u64*>(pwst + " << pw_words << "u);\n"
        "  const u32 c0 = blockIdx.x * BLOCK, pt = threadIdx.x % BLOCK, grp = threadIdx.x / BLOCK;\n"
+       "  const u32 pwsm = saddr(pwst + grp * " << (size_t)unit_terms * 4 << "u);\n"
        "  if (threadIdx.x == 0) { mbar_init(full, 1u); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }\n  __syncthreads();\n"
        "  if (threadIdx.x == 0) {\n    mbar_expect_tx(full, " << col_words * 4 << "u);\n";
   for (auto& kv : slot) o << "    copy_col(zkb_sm + " << (size_t)kv.second * rowp << "u, g" << kv.first.first << " + (size_t)" << kv.first.second << " * dom, c0, mask, full);\n";
@@ -746,6 +774,201 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
   prog.threads = gi.block;
   return true;
 }
+// ---- compact form: the flat form with the PROGRAM AS DATA ---------------------------------------------------------------------
+// ncu on the PTX flat form (profiles/r2_f_heavy_ec_ncu.txt): 8.6 of 12.2 cycles per issued instruction are "no instruction" stalls --
+// 9 MB of straight-line code pass through the instruction caches once per 128-point tile and each warp waits for every line; only
+// 4 warps per scheduler fit next to the 161 KB tile, so the latency is not hidden.  But the 20 k terms of a real constraint system
+// have very few SHAPES (SYN-HEAVY: a - (x + k y) with and without a global; rv32im: a few hundred patterns repeated per instruction
+// class).  Here each distinct expression shape is compiled ONCE as a loop body and the terms become operand records
+// (shared-memory offsets of the taps, constants, global indices) in a read-only table: the instruction stream is a few KB and stays
+// in the L0 / L1.5 instruction caches; per unit a warp group stages its slice of the operand table and of the poly_mix powers in
+// shared memory (uniform, broadcast loads).  Terms of a group are sorted by shape, so a group is a handful of runs.
+//   record layout (uint4 granules): unit = [n_groups,0,0,0] groups...; group = [n_conds, n_runs, 0, 0] [cond tap offsets...]
+//   runs...; run = [shape, count, 0, 0] terms...; term = ceil(leaves / 4) granules of operands in depth-first order.
+// Applies when every AndCond condition is a plain tap and no expression has more than 16 leaves; otherwise the PTX flat form is used.
+struct CompactShape { std::string expr; uint32_t leaves = 0; };
+static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src) {
+  const size_t n = c.steps.size();
+  std::vector<size_t> fp_step(c.n_fp_vars), mx_step(c.n_mix_vars);
+  { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) fp_step[fi++] = i; else mx_step[mi++] = i; } }
+  std::vector<uint32_t> mpow(c.n_mix_vars, 0);
+  for (uint32_t m = 0; m < c.n_mix_vars; ++m) {
+    const StepDef& s = c.steps[mx_step[m]];
+    if (s.op == PX_AND_EQZ) mpow[m] = mpow[s.a] + 1; else if (s.op == PX_AND_COND) mpow[m] = mpow[s.a] + mpow[s.c];
+  }
+  std::vector<std::vector<uint32_t>> cls(1);
+  std::map<std::vector<uint32_t>, uint32_t> cl_id{{{}, 0u}};
+  struct Term { uint32_t power, cl, value, shape; std::vector<uint32_t> ops; };
+  std::vector<Term> terms;
+  struct Item { uint32_t m, off, cl; };
+  std::vector<Item> stack{{c.ret, 0u, 0u}};
+  while (!stack.empty()) {
+    Item it = stack.back(); stack.pop_back();
+    for (;;) {
+      const StepDef& s = c.steps[mx_step[it.m]];
+      if (s.op == PX_TRUE) break;
+      if (s.op == PX_AND_EQZ) { terms.push_back({it.off + mpow[s.a], it.cl, s.b, 0, {}}); it.m = s.a; continue; }
+      if (c.steps[fp_step[s.b]].op != PX_GET) return false;               // conditions must be plain taps
+      std::vector<uint32_t> inner = cls[it.cl]; inner.push_back(s.b);
+      auto f = cl_id.find(inner);
+      uint32_t id;
+      if (f == cl_id.end()) { id = (uint32_t)cls.size(); cl_id.emplace(inner, id); cls.push_back(inner); } else id = f->second;
+      stack.push_back({s.c, it.off + mpow[s.a], id});
+      it.m = s.a;
+    }
+  }
+  if (terms.empty()) return false;
+  // columns
+  std::map<std::pair<uint32_t, uint32_t>, uint32_t> slot;
+  uint32_t halo = 0;
+  for (const TapDef& t : c.taps) { slot.emplace(std::make_pair(t.group, t.column), 0u); halo = std::max(halo, 4 * t.back); }
+  { uint32_t k = 0; for (auto& kv : slot) kv.second = k++; }
+  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", 4, 1, 8);
+  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", 256, 8, 512);
+  const uint32_t unit_vecs = env_u32("ZKB_EC_UNIT_VECS", 640, 64, 4096);          // operand-table granules (16 B) a unit may use
+  uint32_t points = env_u32("ZKB_EC_FLAT_POINTS", 128, 32, 512);
+  const size_t stage_words = (size_t)groups * ((size_t)unit_terms + unit_vecs) * 4;
+  while (points > 32 && ((size_t)slot.size() * (points + halo) * 4 + (size_t)(groups - 1) * points * 16 + stage_words * 4 + 64 > 220 * 1024)) points >>= 1;
+  const uint32_t rowp = points + halo;
+  const size_t col_words = (size_t)slot.size() * rowp;
+  gi.smem = col_words * 4 + (size_t)(groups - 1) * points * 16 + stage_words * 4 + 16;
+  if (gi.smem > 220 * 1024 || (halo & 3)) return false;
+  // BYTE offset of a tap from the thread's row in column slot 0: the load is then one add + LDS (word offsets cost IMAD.IADD + LEA + LDS)
+  auto tap_off = [&](const TapDef& t) { return (uint32_t)(int32_t)(4 * ((long)slot[{t.group, t.column}] * rowp - 4 * (long)t.back)); };
+  // shapes
+  std::map<std::string, uint32_t> shape_id;
+  std::vector<CompactShape> shapes;
+  bool too_big = false;
+  std::function<std::string(uint32_t, std::vector<uint32_t>&)> walk = [&](uint32_t f, std::vector<uint32_t>& ops) -> std::string {
+    const StepDef& s = c.steps[fp_step[f]];
+    if (ops.size() > 16) { too_big = true; return "0u"; }
+    const std::string leaf = "L(" + std::to_string(ops.size()) + ")";
+    switch (s.op) {
+      case PX_CONST: ops.push_back(Fp::from(s.a).v); return leaf;
+      case PX_GET: ops.push_back(tap_off(c.taps[s.a])); return "TAP(" + leaf + ")";
+      case PX_GET_GLOBAL: ops.push_back(s.a == 0 ? s.b : c.mix_size + s.b); return "GL(" + leaf + ")";
+      default: break;
+    }
+    std::string x = walk(s.a, ops), y = walk(s.b, ops);
+    return std::string(s.op == PX_ADD ? "add(" : s.op == PX_SUB ? "sub(" : "mul(") + x + ", " + y + ")";
+  };
+  for (Term& t : terms) {
+    std::string e = walk(t.value, t.ops);
+    if (too_big || t.ops.size() > 16) return false;
+    auto f = shape_id.find(e);
+    if (f == shape_id.end()) { f = shape_id.emplace(e, (uint32_t)shapes.size()).first; shapes.push_back({e, (uint32_t)t.ops.size()}); }
+    t.shape = f->second;
+  }
+  if (shapes.size() > env_u32("ZKB_EC_MAX_SHAPES", 512, 1, 1u << 20)) return false;
+  std::stable_sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) { return x.cl != y.cl ? x.cl < y.cl : x.shape != y.shape ? x.shape < y.shape : x.power < y.power; });
+  gi.n_powers = (uint32_t)terms.size();
+  gi.term_power.resize(terms.size());
+  for (size_t t = 0; t < terms.size(); ++t) gi.term_power[t] = terms[t].power;
+  gi.block = (int)(points * groups); gi.points = (int)points; gi.staged = true;
+  // the operand table, unit by unit
+  std::vector<uint32_t> prog;                              // granules of 4 words
+  struct UnitRec { uint32_t off, vecs, term0, nterms; };
+  std::vector<UnitRec> urecs;
+  auto vecs_of = [&](uint32_t leaves) { return std::max<uint32_t>(1, (leaves + 3) / 4); };
+  for (size_t i = 0; i < terms.size();) {
+    UnitRec u{(uint32_t)(prog.size() / 4), 0, (uint32_t)i, 0};
+    const size_t hdr = prog.size(); prog.insert(prog.end(), {0u, 0u, 0u, 0u});
+    uint32_t n_groups = 0;
+    while (i < terms.size()) {
+      // one (possibly partial) group: as many of its terms as still fit the unit
+      const std::vector<uint32_t>& cl = cls[terms[i].cl];
+      const uint32_t ghdr_vecs = 1 + (uint32_t)((cl.size() + 3) / 4);
+      size_t j = i; uint32_t used = (uint32_t)((prog.size() - hdr) / 4) + ghdr_vecs; uint32_t cur_shape = ~0u;
+      while (j < terms.size() && terms[j].cl == terms[i].cl) {
+        uint32_t need = vecs_of(shapes[terms[j].shape].leaves) + (terms[j].shape != cur_shape ? 1u : 0u);
+        if (used + need > unit_vecs || (j - u.term0) >= unit_terms) break;
+        used += need; cur_shape = terms[j].shape; ++j;
+      }
+      if (j == i) { if (n_groups == 0) return false; break; }          // (a single term larger than a unit cannot happen with the limits above)
+      const size_t gh = prog.size();
+      prog.insert(prog.end(), {(uint32_t)cl.size(), 0u, 0u, 0u});
+      for (size_t q = 0; q < (cl.size() + 3) / 4 * 4; ++q) prog.push_back(q < cl.size() ? tap_off(c.taps[c.steps[fp_step[cl[q]]].a]) : 0u);
+      uint32_t n_runs = 0;
+      for (size_t k = i; k < j;) {
+        size_t e = k; while (e < j && terms[e].shape == terms[k].shape) ++e;
+        prog.insert(prog.end(), {terms[k].shape, (uint32_t)(e - k), 0u, 0u}); ++n_runs;
+        for (size_t q = k; q < e; ++q) { const uint32_t v = vecs_of(shapes[terms[q].shape].leaves); for (uint32_t w = 0; w < 4 * v; ++w) prog.push_back(w < terms[q].ops.size() ? terms[q].ops[w] : 0u); }
+        k = e;
+      }
+      prog[gh + 1] = n_runs;
+      ++n_groups; i = j;
+      if ((uint32_t)((prog.size() - hdr) / 4) + 3 > unit_vecs || (i - u.term0) >= unit_terms) break;
+    }
+    prog[hdr] = n_groups;
+    u.vecs = (uint32_t)(prog.size() / 4) - u.off; u.nterms = (uint32_t)(i - u.term0);
+    urecs.push_back(u);
+  }
+  // ---- source -----------------------------------------------------------------------------------------------------------------
+  std::ostringstream o;
+  o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
+  o << "#define HALO " << halo << "u\n#define BLOCK " << points << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
+  o << "typedef u64 ACC;\n#define GL(i) __ldg(gl + (i))\n";
+  o << "__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n#define TAP(o) lds32(spb + (o))\n";
+  o << "#define L(i) ((i) < 4 ? (&a0.x)[(i)] : (i) < 8 ? (&a1.x)[(i) - 4] : (i) < 12 ? (&a2.x)[(i) - 8] : (&a3.x)[(i) - 12])\n";
+  o << "__device__ const uint4 zkb_units[" << urecs.size() << "] = {";
+  for (const UnitRec& u : urecs) o << "{" << u.off << "u," << u.vecs << "u," << u.term0 << "u," << u.nterms << "u},";
+  o << "};\n__device__ const uint4 zkb_prog[" << prog.size() / 4 << "] = {\n";
+  for (size_t q = 0; q < prog.size(); q += 4) o << "{" << prog[q] << "u," << prog[q + 1] << "u," << prog[q + 2] << "u," << prog[q + 3] << "u}," << ((q / 4) % 8 == 7 ? "\n" : "");
+  o << "};\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << gi.block << ", 1) zkb_ec(u32* __restrict__ check, const u32* __restrict__ g0, const u32* __restrict__ g1, "
+       "const u32* __restrict__ g2, const uint4* __restrict__ pw, const u32* __restrict__ gl, uint4 invden, u32 mask) {\n"
+       "  size_t dom; asm(\"add.u64 %0, %1, 1;\" : \"=l\"(dom) : \"l\"((u64)mask));\n"
+       "  extern __shared__ __align__(128) u32 zkb_sm[];\n"
+       "  u32* const part = zkb_sm + " << col_words << "u;\n"
+       "  uint4* const stage = reinterpret_cast<uint4*>(part + " << (size_t)(groups - 1) * points * 4 << "u);\n"
+       "  u64* const full = reinterpret_cast<u64*>(part + " << (size_t)(groups - 1) * points * 4 + stage_words << "u);\n"
+       "  const u32 c0 = blockIdx.x * BLOCK, pt = threadIdx.x % BLOCK, grp = threadIdx.x / BLOCK;\n"
+       "  uint4* const dsm = stage + grp * " << (unit_terms + unit_vecs) << "u;      // this warp group's operand records ...\n"
+       "  uint4* const wsm = dsm + " << unit_vecs << "u;                              // ... and poly_mix powers of the unit it is running\n"
+       "  if (threadIdx.x == 0) { mbar_init(full, 1u); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }\n  __syncthreads();\n"
+       "  if (threadIdx.x == 0) {\n    mbar_expect_tx(full, " << col_words * 4 << "u);\n";
+  for (auto& kv : slot) o << "    copy_col(zkb_sm + " << (size_t)kv.second * rowp << "u, g" << kv.first.first << " + (size_t)" << kv.first.second << " * dom, c0, mask, full);\n";
+  o << "  }\n  mbar_wait(full, 0u);\n  const u32 spb = saddr(zkb_sm + pt + HALO);          // shared-window byte address of this thread's row in column slot 0\n  u32 ra = 0u, rb = 0u, rc = 0u, rd = 0u;\n"
+       "  for (u32 u = grp; u < " << urecs.size() << "u; u += " << groups << "u) {\n"
+       "    const uint4 ur = zkb_units[u];\n"
+       "    asm volatile(\"bar.sync %0, " << points << ";\" :: \"r\"(grp + 1u) : \"memory\");          // the group is done with the previous unit's records\n"
+       "    for (u32 i = pt; i < ur.y; i += BLOCK) dsm[i] = zkb_prog[ur.x + i];\n"
+       "    for (u32 i = pt; i < ur.w; i += BLOCK) wsm[i] = __ldg(pw + ur.z + i);\n"
+       "    asm volatile(\"bar.sync %0, " << points << ";\" :: \"r\"(grp + 1u) : \"memory\");\n"
+       "    const uint4* d = dsm; const uint4* w = wsm;\n"
+       "    const u32 n_groups = d->x; ++d;\n"
+       "    for (u32 g = 0; g < n_groups; ++g) {\n"
+       "      const u32 n_conds = d->x, n_runs = d->y; ++d;\n"
+       "      u32 cp = 0u;\n"
+       "      for (u32 q = 0; q < n_conds; ++q) { const u32 cv = TAP(reinterpret_cast<const u32*>(d)[q]); cp = q ? mul(cp, cv) : cv; }\n"
+       "      d += (n_conds + 3u) >> 2;\n"
+       "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0; u32 k = 0u;\n"
+       "      for (u32 r = 0; r < n_runs; ++r) {\n"
+       "        const u32 shape = d->x, count = d->y; ++d;\n"
+       "        switch (shape) {\n";
+  for (size_t sidx = 0; sidx < shapes.size(); ++sidx) {
+    const uint32_t v = vecs_of(shapes[sidx].leaves);
+    o << "          case " << sidx << ": for (u32 i = 0; i < count; ++i) {\n            const uint4 a0 = d[0]";
+    for (uint32_t q = 1; q < 4; ++q) o << ", a" << q << " = " << (q < v ? "d[" + std::to_string(q) + "]" : std::string("a0"));
+    o << "; d += " << v << ";\n            const u32 v = " << shapes[sidx].expr << ";\n"
+         "            const uint4 m = *w++; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w);\n"
+         "            if (k++ & 1u) { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); }\n          } break;\n";
+  }
+  o << "        }\n      }\n"
+       "      const u32 la = fin(A0), lb = fin(A1), lc = fin(A2), ld = fin(A3);\n"
+       "      if (n_conds) { ra = add(ra, mul(la, cp)); rb = add(rb, mul(lb, cp)); rc = add(rc, mul(lc, cp)); rd = add(rd, mul(ld, cp)); }\n"
+       "      else { ra = add(ra, la); rb = add(rb, lb); rc = add(rc, lc); rd = add(rd, ld); }\n"
+       "    }\n  }\n";
+  if (groups > 1) o << "  if (grp) { uint4* q = reinterpret_cast<uint4*>(part) + (grp - 1u) * BLOCK + pt; *q = make_uint4(ra, rb, rc, rd); }\n  __syncthreads();\n  if (grp) return;\n"
+                       "  for (u32 g = 0; g < " << groups - 1 << "u; ++g) { const uint4 q = reinterpret_cast<const uint4*>(part)[g * BLOCK + pt]; ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
+  o << "  const u32 c = c0 + pt;\n"
+       "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n"
+       "  st(check + c, mul(ra, den)); st(check + dom + c, mul(rb, den)); st(check + 2 * dom + c, mul(rc, den)); st(check + 3 * dom + c, mul(rd, den));\n}\n";
+  src = o.str();
+  return true;
+}
+static bool compact_wanted() { const char* e = getenv("ZKB_EC_FORM"); return !(e && !strcmp(e, "flat")); }      // ZKB_EC_FORM=flat forces the PTX flat form
+
 static std::string flat_text(const FlatProgram& p) { std::string t = p.main_cu; for (const std::string& u : p.unit_ptx) { t += "\n//----\n"; t += u; } return t; }
 
 // ---- on-disk cubin cache -------------------------------------------------------------------------------------------------
@@ -1014,7 +1237,11 @@ bool accumulate_jit(zkb_ctx* ctx, const CircuitDef& c, size_t phase, uint32_t* d
 // The generated source (for tests / inspection) -- no device needed.
 std::string eval_jit_source(const CircuitDef& c) {
   GenInfo gi;
-  if (flat_wanted(c)) { FlatProgram fp; if (generate_flat(c, gi, fp)) return flat_text(fp); }
+  if (flat_wanted(c)) {
+    std::string cs;
+    if (compact_wanted() && generate_compact(c, gi, cs)) return cs;
+    FlatProgram fp; if (generate_flat(c, gi, fp)) return flat_text(fp);
+  }
   if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty()) return src; }
   return generate(c, gi, false);
 }
@@ -1025,7 +1252,11 @@ bool eval_jit_compile_only(const CircuitDef& c, std::string& why) {
   std::vector<char> cubin; GenInfo gi;
   if (!c.wsteps.empty() && !compile(accumulate_jit_source(c), cubin, why)) return false;      // the witness program's phase kernels
   // heavy circuits: the flat form only (the straight-line forms of a 10^5-step program take ptxas tens of minutes and spill)
-  if (flat_wanted(c)) { FlatProgram fp; if (generate_flat(c, gi, fp)) return compile_flat(fp, cubin, why); }
+  if (flat_wanted(c)) {
+    std::string cs;
+    if (compact_wanted() && generate_compact(c, gi, cs)) return compile(cs, cubin, why);
+    FlatProgram fp; if (generate_flat(c, gi, fp)) return compile_flat(fp, cubin, why);
+  }
   // every form a proof may use: the staged kernel, and the register form used for tiny domains / unaligned sub-buffers
   if (ec_staged()) { std::string src = generate(c, gi, true); if (!src.empty() && !compile(src, cubin, why)) return false; }
   return compile(generate(c, gi, false), cubin, why);
@@ -1040,7 +1271,10 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool s
   GenInfo gi;
   FlatProgram fprog;
   std::string src;
-  if (flat) { if (generate_flat(c, gi, fprog)) src = flat_text(fprog); } else src = generate(c, gi, staged);
+  bool ptx_flat = false;      // the PTX flat form goes through nvJitLink; everything else is one NVRTC program
+  if (flat) {
+    if (!(compact_wanted() && generate_compact(c, gi, src))) { src.clear(); if (generate_flat(c, gi, fprog)) { src = flat_text(fprog); ptx_flat = true; } }
+  } else src = generate(c, gi, staged);
   if (src.empty()) { why = flat ? "circuit does not fit the flat form" : "circuit does not fit the staged form"; return nullptr; }
   const uint32_t np = gi.n_powers;
   uint64_t key = fnv1a(src);
@@ -1048,13 +1282,13 @@ static const EvalJitKernel* get_kernel(zkb_ctx* ctx, const CircuitDef& c, bool s
   if (it != cache->kernels.end()) return &it->second;
   if (cache->failed.count(key)) { why = "previous JIT attempt failed"; return nullptr; }
   std::vector<char> cubin;
-  EvalJitKernel k; k.n_powers = np; k.block = gi.block; k.smem = gi.smem; k.points = gi.points ? gi.points : gi.block;
-  if (!(flat ? compile_flat(fprog, cubin, why) : compile(src, cubin, why))) { cache->failed[key] = true; return nullptr; }
+  EvalJitKernel k; k.n_powers = np; k.block = gi.block; k.smem = gi.smem; k.points = gi.points ? gi.points : gi.block; k.term_power = gi.term_power;
+  if (!(ptx_flat ? compile_flat(fprog, cubin, why) : compile(src, cubin, why))) { cache->failed[key] = true; return nullptr; }
   ZKB_CUDA(cudaFree(0));     // make sure the primary context is current for the driver API
   CUresult r = a.moduleLoadData(&k.mod, cubin.data());
   if (r != CUDA_SUCCESS) {      // a cached cubin that does not load (other driver, damaged file) is a cache miss: drop it, recompile once
     cubin.clear();
-    if (!(flat ? compile_flat(fprog, cubin, why, /*ignore_disk=*/true) : compile(src, cubin, why, /*ignore_disk=*/true))) { cache->failed[key] = true; return nullptr; }
+    if (!(ptx_flat ? compile_flat(fprog, cubin, why, /*ignore_disk=*/true) : compile(src, cubin, why, /*ignore_disk=*/true))) { cache->failed[key] = true; return nullptr; }
     r = a.moduleLoadData(&k.mod, cubin.data());
   }
   if (r == CUDA_SUCCESS) r = a.moduleGetFunction(&k.fn, k.mod, "zkb_ec");
@@ -1089,7 +1323,15 @@ bool eval_check_jit(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const 
   // per-proof data: [powers of poly_mix (4 words each)] [mix globals] [out globals]
   std::vector<uint32_t> h(4 * (size_t)k->n_powers + c.mix_size + c.out_size + 4);
   Fp4 cur = Fp4::one();
-  for (uint32_t i = 0; i < k->n_powers; ++i) { cur.store(&h[4 * i]); cur *= poly_mix; }
+  if (k->term_power.empty()) {
+    for (uint32_t i = 0; i < k->n_powers; ++i) { cur.store(&h[4 * i]); cur *= poly_mix; }
+  } else {      // flat form: powers gathered into term order
+    uint32_t maxp = 0;
+    for (uint32_t pw_ : k->term_power) maxp = std::max(maxp, pw_);
+    std::vector<Fp4> pows(maxp + 1);
+    for (uint32_t i = 0; i <= maxp; ++i) { pows[i] = cur; cur *= poly_mix; }
+    for (size_t t = 0; t < k->term_power.size(); ++t) pows[k->term_power[t]].store(&h[4 * t]);
+  }
   uint32_t* gl = h.data() + 4 * (size_t)k->n_powers;
   for (uint32_t i = 0; i < c.mix_size; ++i) gl[i] = mix_g[i];
   for (uint32_t i = 0; i < c.out_size; ++i) gl[c.mix_size + i] = out_g[i];

@@ -238,7 +238,12 @@ template <int A, int TL = 0> struct STile {
 // shared by all columns and stays in L2.
 // SL: log2 S as a compile-time constant (0 = take it from args): every global access of the tile is then base + immediate
 // (the 32 loads / stores of a thread cost ~80 address instructions otherwise -- 7 % of the kernel's issue slots).
-template <int A, bool INV, int TL = 0, bool TAB = false, int SL = 0>
+// TAB = 2 (forward): FACTORED tables.  rev_A(16 t + r) = rev4(r) 2^(A-4) + rev_{A-4}(t), so the factor of register r is
+// gtab[r][p2] * vtab[t][p2] with gtab[r][p2] = w_M^(rev4(r) 2^(A-4) p2) (16 x S Shoup pairs, 512 KB: the 8 columns of a tile are
+// 1 KB, L1-resident) and vtab[t][p2] = w_M^(rev_{A-4}(t) p2) (2^(A-4) x S pairs, 2 MB, one load per thread): two Shoup products per
+// element (8 multiplier-pipe slots, no ALU work) instead of the running product's two Montgomery products (10 slots + 6 ALU
+// instructions) and without the full table's 8 bytes of L2 traffic per element.
+template <int A, bool INV, int TL = 0, int TAB = 0, int SL = 0>
 __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __restrict__ io, const uint2* __restrict__ twl, TwiddleRef tw, const uint32_t* __restrict__ table, SArgs args,
                                                                  const uint2* __restrict__ ttab, const uint32_t* __restrict__ src, uint32_t ones) {
   constexpr int T_LOG = STile<A, TL>::T_LOG, T = STile<A, TL>::T, TPB = (1 << A) / 16;
@@ -261,7 +266,13 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   // inter-pass twiddles: register r (holding local position 16 t + r) needs G^(rev_A(16 t + r)) = V * g^(rev4(r)),
   // G = w_M^(+-p2) [* shift base], V = G^(rev_{A-4}(t)), g = G^(2^(A-4)).
   auto twiddle_all = [&](bool inverse) {
-    if (TAB) {
+    if (TAB == 2) {
+      const uint2 V = __ldg(ttab + ((size_t)16 << s_log) + ((size_t)t << s_log) + p2);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = shoup_lazy(shoup_lazy(v[r], __ldg(ttab + ((size_t)r << s_log) + p2)), V);
+      return;
+    }
+    if (TAB == 1) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         uint32_t x = shoup_lazy(v[r], __ldg(ttab + off_c + ((size_t)r << s_log)));
@@ -340,6 +351,18 @@ __global__ void __launch_bounds__(STile<A, TL>::THREADS) k_ntt_s(uint32_t* __res
   }
 }
 
+// factored forward tables (k_ntt_s TAB = 2): [16 x S] g-part, then [2^(a-4) x S] v-part
+__global__ void k_ntt_s_table2(uint2* __restrict__ out, TwiddleRef tw, int a, int s_log) {
+  const uint32_t m_log = (uint32_t)(a + s_log), S = 1u << s_log;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, total = (16u + (1u << (a - 4))) << s_log;
+  if (idx >= total) return;
+  const uint32_t row = idx >> s_log, p2 = idx & (S - 1u);
+  const uint32_t j = row < 16u ? (bit_rev32(row, 4) << (a - 4)) : bit_rev32(row - 16u, a - 4);
+  const uint32_t e = (j * p2) & ((1u << m_log) - 1u);
+  const uint32_t plain = mont_mul(tw.fwd(e, (int)m_log), 1u);
+  out[idx] = make_uint2(plain, (uint32_t)(((uint64_t)plain << 32) / P));
+}
+
 // ttab[l * S + p2] for one strided pass (see k_ntt_s TAB)
 __global__ void k_ntt_s_table(uint2* __restrict__ out, TwiddleRef tw, int a, int s_log, int inverse, uint32_t shift_base, uint32_t mult) {
   const uint32_t m_log = (uint32_t)(a + s_log);
@@ -371,6 +394,24 @@ static const uint2* s_pass_table(zkb_ctx* ctx, int a, int s_log, bool inverse, F
   uint32_t* d = nullptr;
   ZKB_CUDA(cudaMalloc((void**)&d, m * 8));
   k_ntt_s_table<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>((uint2*)d, tw, a, s_log, inverse ? 1 : 0, shift_base.v, mult.v);
+  launched(ctx);
+  t->s_tables[key] = d;
+  return (const uint2*)d;
+}
+
+// 0 = running product, 1 = factored tables (default; a >= 5 only), 2 = full table
+static int s_fwd_mode() { static int v = [] { const char* e = getenv("ZKB_NTT_S_FWD"); return e ? atoi(e) : 1; }(); return v; }
+static const uint2* s_pass_table2(zkb_ctx* ctx, int a, int s_log) {
+  if (s_fwd_mode() != 1 || a < 5 || a + s_log > 26) return nullptr;
+  NttTables* t = ntt_tables(ctx);
+  uint64_t key = 0x6000000000000000ull ^ ((uint64_t)a << 52) ^ ((uint64_t)s_log << 44);
+  auto it = t->s_tables.find(key);
+  if (it != t->s_tables.end()) return (const uint2*)it->second;
+  TwiddleRef tw{t->d_hi, t->d_lo};
+  size_t m = ((size_t)16 + ((size_t)1 << (a - 4))) << s_log;
+  uint32_t* d = nullptr;
+  ZKB_CUDA(cudaMalloc((void**)&d, m * 8));
+  k_ntt_s_table2<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>((uint2*)d, tw, a, s_log);
   launched(ctx);
   t->s_tables[key] = d;
   return (const uint2*)d;
@@ -432,34 +473,36 @@ static bool make_plan(int k, Plan& pl) {
 }
 
 template <int A, bool INV, int TL = 0>
-static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src) {
+static void launch_s(zkb_ctx* ctx, uint32_t* io, size_t total_elems, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src, int tab_mode) {
   using ST = STile<A, TL>;
   SArgs args{(uint32_t)s_log, (uint32_t)(s_log - ST::T_LOG), shift_g, table ? 1u : 0u};
   size_t tile_elems = (size_t)(1 << A) * ST::T;
   size_t smem = (size_t)phys_size((uint32_t)tile_elems) * 4;
-  auto kern = s_log == 12 ? (ttab ? k_ntt_s<A, INV, TL, true, 12> : k_ntt_s<A, INV, TL, false, 12>) : (ttab ? k_ntt_s<A, INV, TL, true> : k_ntt_s<A, INV, TL, false>);
+  if (!ttab) tab_mode = 0;
+  auto kern = s_log == 12 ? (tab_mode == 2 ? k_ntt_s<A, INV, TL, 2, 12> : tab_mode == 1 ? k_ntt_s<A, INV, TL, 1, 12> : k_ntt_s<A, INV, TL, 0, 12>)
+                          : (tab_mode == 2 ? k_ntt_s<A, INV, TL, 2> : tab_mode == 1 ? k_ntt_s<A, INV, TL, 1> : k_ntt_s<A, INV, TL, 0>);
   if (smem > 48 * 1024) ZKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(total_elems / tile_elems), ST::THREADS, smem, ctx->stream>>>(io, twl, tw, table, args, ttab, src, ntt_ones());
   launched(ctx);
 }
 static int s_tile_log() { static int v = [] { const char* e = getenv("ZKB_NTT_S_TLOG"); return e ? atoi(e) : 3; }(); return v; }
 template <bool INV>
-static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src = nullptr) {
+static void dispatch_s(zkb_ctx* ctx, int a, uint32_t* io, size_t total, int s_log, const uint2* twl, TwiddleRef tw, const uint32_t* table, uint32_t shift_g, const uint2* ttab, const uint32_t* src = nullptr, int tab_mode = 1) {
   switch (a) {
-    case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
-    case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
-    case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
-    case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
-    case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src); break;
+    case 4: launch_s<4, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode); break;
+    case 5: launch_s<5, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode); break;
+    case 6: launch_s<6, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode); break;
+    case 7: launch_s<7, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode); break;
+    case 8: launch_s<8, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode); break;
     case 9:
-      if (s_tile_log() == 3) launch_s<9, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
-      else if (s_tile_log() == 2) launch_s<9, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
-      else launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      if (s_tile_log() == 3) launch_s<9, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
+      else if (s_tile_log() == 2) launch_s<9, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
+      else launch_s<9, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
       break;
     case 10:
-      if (s_tile_log() == 3) launch_s<10, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
-      else if (s_tile_log() == 2) launch_s<10, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
-      else launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src);
+      if (s_tile_log() == 3) launch_s<10, INV, 3>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
+      else if (s_tile_log() == 2) launch_s<10, INV, 2>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
+      else launch_s<10, INV>(ctx, io, total, s_log, twl, tw, table, shift_g, ttab, src, tab_mode);
       break;
     default: throw Error("zkb200: unsupported strided NTT size");
   }
@@ -566,7 +609,9 @@ bool ntt_forward_tiled(zkb_ctx* ctx, uint32_t* out, const uint32_t* in, size_t c
     // strided passes, innermost first: pass i works inside blocks of 2^(a_c + a_s[n_s-1] + ... + a_s[i]) elements
     int s_log = pl.a_c;
     for (int i = pl.n_s - 1; i >= 0; --i) {
-      dispatch_s<false>(ctx, pl.a_s[i], o, total, s_log, twl, tw, nullptr, R_MOD_P, s_pass_table(ctx, pl.a_s[i], s_log, false, Fp::one(), Fp::one()));
+      const uint2* t2 = s_pass_table2(ctx, pl.a_s[i], s_log);
+      if (t2) dispatch_s<false>(ctx, pl.a_s[i], o, total, s_log, twl, tw, nullptr, R_MOD_P, t2, nullptr, 2);
+      else dispatch_s<false>(ctx, pl.a_s[i], o, total, s_log, twl, tw, nullptr, R_MOD_P, s_pass_table(ctx, pl.a_s[i], s_log, false, Fp::one(), Fp::one()));
       s_log += pl.a_s[i];
     }
   }
