@@ -180,6 +180,18 @@ zkb_err zkb_prover_stage_wait(zkb_prover* p);
 zkb_err zkb_verify_segment(const uint32_t* h_circuit, size_t circuit_words, const uint32_t* h_seal, size_t seal_words,
                            const uint32_t* h_control_ids, size_t n_control_ids, uint32_t* h_out_po2_code_root);
 
+/* ---- poseidon_254 hash suite (first slice of SURVEY.md 8f-4: the suite identity_p254 / the Groth16 wrapper use) --------------------
+ * Poseidon over the BN254 scalar field, t = 3, x^5, R_F = 8, R_P = 57 = circomlib's 2-input `poseidon`; constants regenerated from the
+ * reference Grain LFSR and pinned by circomlib's public known answers.  Digests are 8 little-endian u32 words holding the canonical
+ * field element.  hash_fold / merkle_build follow risc0's hash_pair (poseidon([0, a, b])[0]); hash_rows uses a PROVISIONAL packing of
+ * the row (8 canonical BabyBear values per word in radix 2^31, rate 2, overwrite mode, zero padding) -- upstream's rule is not
+ * recoverable offline (zktls_b200/csrc/k_poseidon254.cu). */
+zkb_err zkb_poseidon254_hash_rows(zkb_ctx* ctx, void* d_out_digests, const void* d_matrix, size_t rows, size_t cols);
+zkb_err zkb_poseidon254_hash_fold(zkb_ctx* ctx, void* d_nodes, size_t input_size, size_t output_size);
+zkb_err zkb_poseidon254_merkle_build(zkb_ctx* ctx, void* d_nodes, size_t rows);
+/* host-only known-answer hook: one permutation of three canonical field elements (3 x 8 words in, 3 x 8 words out) */
+zkb_err zkb_poseidon254_permute_host(const uint32_t* h_in, uint32_t* h_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,10 @@ extern "C" {
     pub fn zkb_prove_staged(p: *mut ZkbProver, h_io: *const u32) -> ZkbErr;
     pub fn zkb_prover_stage_wait(p: *mut ZkbProver) -> ZkbErr;
     pub fn zkb_verify_segment(h_circuit: *const u32, circuit_words: usize, h_seal: *const u32, seal_words: usize, h_control_ids: *const u32, n_control_ids: usize, h_out_po2_code_root: *mut u32) -> ZkbErr;
+    pub fn zkb_poseidon254_hash_rows(ctx: *mut ZkbCtx, d_out_digests: *mut c_void, d_matrix: *const c_void, rows: usize, cols: usize) -> ZkbErr;
+    pub fn zkb_poseidon254_hash_fold(ctx: *mut ZkbCtx, d_nodes: *mut c_void, input_size: usize, output_size: usize) -> ZkbErr;
+    pub fn zkb_poseidon254_merkle_build(ctx: *mut ZkbCtx, d_nodes: *mut c_void, rows: usize) -> ZkbErr;
+    pub fn zkb_poseidon254_permute_host(h_in: *const u32, h_out: *mut u32) -> ZkbErr;
 }
 
 /// NULL = Ok; otherwise copy the message, free it with zkb_free_error and return it as an error (risc0-sys `ffi_wrap`).

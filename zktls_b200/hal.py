@@ -160,6 +160,17 @@ class B200Hal:
     def merkle_build(self, nodes, rows):
         check(lib().zkb_poseidon2_merkle_build(self.ctx, C.c_void_p(nodes.ptr), _sz(rows)))
 
+    # ---- poseidon_254 suite (identity_p254's hash; first slice, see include/zkb200.h) ----------------------------------------
+    def p254_hash_rows(self, out, matrix):
+        rows = out.size; cols = matrix.size // rows if rows else 0
+        check(lib().zkb_poseidon254_hash_rows(self.ctx, C.c_void_p(out.ptr), C.c_void_p(matrix.ptr), _sz(rows), _sz(cols)))
+
+    def p254_hash_fold(self, io, input_size, output_size):
+        check(lib().zkb_poseidon254_hash_fold(self.ctx, C.c_void_p(io.ptr), _sz(input_size), _sz(output_size)))
+
+    def p254_merkle_build(self, nodes, rows):
+        check(lib().zkb_poseidon254_merkle_build(self.ctx, C.c_void_p(nodes.ptr), _sz(rows)))
+
     # ---- mixing / DEEP / FRI -----------------------------------------------------------------------------------
     def batch_evaluate_any(self, coeffs, poly_count, which, xs, out):
         po2 = self._po2(coeffs.size // poly_count)
