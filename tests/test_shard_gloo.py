@@ -56,6 +56,44 @@ def test_two_ranks_gather_the_same_session(tmp_path):
     assert digests[0] == single, "sharded result differs from the single-process result"
 
 
+def _queue_worker(rank, world, port, n_segments, out_dir):
+    import threading
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q = shard.SharedSegmentQueue(n_segments, "t0")
+    dist.barrier()
+    taken = []
+    def work():
+        while True:
+            i = q.take()
+            if i is None:
+                return
+            taken.append(i)
+            if rank == 0:          # rank 0 is the "slow" rank: it must end up with fewer segments, not hold the others back
+                import time; time.sleep(0.02)
+    ths = [threading.Thread(target=work) for _ in range(3)]          # three workers per rank, as bench.py runs them
+    for t in ths: t.start()
+    for t in ths: t.join()
+    local = {s: np.full(4, s, dtype=np.uint32) for s in taken}
+    results = shard.gather_results(local, n_segments, rank, world, dist)      # raises on a missing or doubly taken segment
+    assert [int(r[0]) for r in results] == list(range(n_segments))
+    with open(os.path.join(out_dir, f"taken{rank}.txt"), "w") as f:
+        f.write(" ".join(str(s) for s in sorted(taken)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_queue_hands_every_segment_to_exactly_one_rank(tmp_path):
+    n_segments, world = 40, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_queue_worker, args=(world, port, n_segments, str(tmp_path)), nprocs=world, join=True)
+    taken = [[int(x) for x in open(tmp_path / f"taken{r}.txt").read().split()] for r in range(world)]
+    assert sorted(taken[0] + taken[1]) == list(range(n_segments))
+    assert len(taken[0]) < len(taken[1]), "the slow rank should have taken fewer segments"
+
+
 def test_gather_detects_missing_and_duplicate_segments():
     class FakeDist:
         def __init__(self, parts): self.parts = parts

@@ -30,5 +30,19 @@ seal = pr.finish(accum_m); verify_segment(blob, seal, control_id(po2, pr.roots()
 tr = synth.trace_a(shape, po2, 5)
 pr.stage(po2, *tr[1:]); pr.stage(po2, *tr[1:]); s1 = pr.prove_staged(tr[0]); s2 = pr.prove_staged(tr[0])
 assert np.array_equal(s1, s2)
-pr.close(); hal.sync(); hal.close()
+pr.close()
+# round 2: device-side accumulate (witness program as data), the heavy-circuit forms of eval_check, the poseidon_254 kernels
+d_acc = hal.copy_from_elem(accum_m)
+hal.accumulate(blob, d_acc, hal.copy_from_elem(code_m), hal.copy_from_elem(data_m), mix, io, po2)
+red = dict(accum_cols=6, code_cols=6, data_cols=12, mix_size=5, out_size=4, majors=2, fanout=(2, 2, 2), leaf_constraints=6)
+hb = circuit.syn_heavy_circuit(**red); hblob = hb.blob()
+for form in ("compact", "flat"):
+    os.environ["ZKB_EC_FORM"] = form
+    dom = 4 << 7
+    chk = hal.alloc_elem(4 * dom)
+    hal.eval_check(chk, hblob, *[hal.copy_from_elem(fp(n * dom)) for n in hb.group_size], fp(5), fp(4), fp(4), 7)
+os.environ.pop("ZKB_EC_FORM")
+nodes = hal.copy_from_digest(fp(2 * 64 * 8) & 0x0fffffff); hal.p254_merkle_build(nodes, 64)
+pd = hal.alloc_digest(33); hal.p254_hash_rows(pd, hal.copy_from_elem(fp(33 * 9)))
+hal.sync(); hal.close()
 print("sanitize smoke ok")

@@ -62,4 +62,15 @@ for po2 in range(16, a.max_po2 + 1, 2):
     by = 96 * (rows - 1); perms = rows - 1
     emit(op="merkle_build", po2=po2, ms=ms, alg_GBps=by / ms / 1e6, hbm_frac=by / ms / 1e6 / HBM, perms_per_s=perms / ms * 1e3, modmul_per_s=1356 * perms / ms * 1e3, int32_frac=1356 * perms / ms * 1e3 / MODMUL)
     del nodes
+# poseidon_254 suite (first slice of SURVEY 8f-4): ~830 256-bit Montgomery products (8 x 8 limb products each) per permutation
+for po2 in (16, 18, 20):
+    rows = 1 << po2
+    nodes = hal.alloc_digest(2 * rows)
+    ms = timed(lambda: hal.p254_merkle_build(nodes, rows), a.reps)
+    emit(op="poseidon254_merkle_build", po2=po2, ms=ms, perms_per_s=(rows - 1) / ms * 1e3)
+    del nodes
+    m = hal.alloc_elem(rows * 16); d = hal.alloc_digest(rows)
+    ms = timed(lambda: hal.p254_hash_rows(d, m), a.reps)
+    emit(op="poseidon254_hash_rows", po2=po2, cols=16, ms=ms, perms_per_s=rows / ms * 1e3, note="provisional row packing: 16 columns = 2 words = 1 permutation")
+    del m, d
 hal.close()

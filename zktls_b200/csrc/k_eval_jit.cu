@@ -909,6 +909,7 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
   o << "#define HALO " << halo << "u\n#define BLOCK " << points << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
   o << "typedef u64 ACC;\n#define GL(i) __ldg(gl + (i))\n";
   o << "__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n#define TAP(o) lds32(spb + (o))\n";
+  o << "#define FIX4 { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); }\n";
   o << "#define L(i) ((i) < 4 ? (&a0.x)[(i)] : (i) < 8 ? (&a1.x)[(i) - 4] : (i) < 12 ? (&a2.x)[(i) - 8] : (&a3.x)[(i) - 12])\n";
   o << "__device__ const uint4 zkb_units[" << urecs.size() << "] = {";
   for (const UnitRec& u : urecs) o << "{" << u.off << "u," << u.vecs << "u," << u.term0 << "u," << u.nterms << "u},";
@@ -942,17 +943,20 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
        "      u32 cp = 0u;\n"
        "      for (u32 q = 0; q < n_conds; ++q) { const u32 cv = TAP(reinterpret_cast<const u32*>(d)[q]); cp = q ? mul(cp, cv) : cv; }\n"
        "      d += (n_conds + 3u) >> 2;\n"
-       "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0; u32 k = 0u;\n"
+       "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0;\n"
        "      for (u32 r = 0; r < n_runs; ++r) {\n"
        "        const u32 shape = d->x, count = d->y; ++d;\n"
        "        switch (shape) {\n";
   for (size_t sidx = 0; sidx < shapes.size(); ++sidx) {
     const uint32_t v = vecs_of(shapes[sidx].leaves);
-    o << "          case " << sidx << ": for (u32 i = 0; i < count; ++i) {\n            const uint4 a0 = d[0]";
-    for (uint32_t q = 1; q < 4; ++q) o << ", a" << q << " = " << (q < v ? "d[" + std::to_string(q) + "]" : std::string("a0"));
-    o << "; d += " << v << ";\n            const u32 v = " << shapes[sidx].expr << ";\n"
-         "            const uint4 m = *w++; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w);\n"
-         "            if (k++ & 1u) { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); }\n          } break;\n";
+    // one term: operands -> value -> four unreduced accumulations; terms are taken in PAIRS with one high-word fix per pair (the accumulators
+    // tolerate two products between fixes), an odd last term gets its own -- no per-term parity test, no predicated fixes
+    std::ostringstream term;
+    term << "{ const uint4 a0 = d[0]";
+    for (uint32_t q = 1; q < 4; ++q) term << ", a" << q << " = " << (q < v ? "d[" + std::to_string(q) + "]" : std::string("a0"));
+    term << "; d += " << v << "; const u32 v = " << shapes[sidx].expr << "; const uint4 m = *w++; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w); }";
+    o << "          case " << sidx << ": {\n            u32 i = 0;\n            for (; i + 2u <= count; i += 2u) {\n              " << term.str() << "\n              " << term.str()
+      << "\n              FIX4\n            }\n            if (i < count) {\n              " << term.str() << "\n              FIX4\n            }\n          } break;\n";
   }
   o << "        }\n      }\n"
        "      const u32 la = fin(A0), lb = fin(A1), lc = fin(A2), ld = fin(A3);\n"

@@ -12,6 +12,7 @@
 #include "ops.cuh"
 #include "transcript.hpp"
 #include <memory>
+#include <mutex>
 #include <time.h>
 
 namespace zkb {
@@ -120,6 +121,22 @@ struct PhaseTimer {
 
 using namespace zkb;
 
+// ONE host->device copy stream per device, shared by every prover of the process: staged uploads are then served FIFO, each at the
+// full link rate, in the order the workers asked for them (= the order their proofs need them).  With a stream per prover the DMA
+// engine interleaves the three workers' 1.17 GB uploads, every one of them lands late, and on a link that is barely fast enough
+// (23 GB/s against the 21.6 GB/s a GPU consumes: GPUs 0-3 of this pool when all eight upload) the proofs wait for their traces.
+static cudaStream_t shared_copy_stream(int device) {
+  static std::mutex mu;
+  static std::map<int, cudaStream_t> streams;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = streams.find(device);
+  if (it != streams.end()) return it->second;
+  cudaStream_t s = nullptr;
+  ZKB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  streams[device] = s;      // lives as long as the process (like the device's memory pool)
+  return s;
+}
+
 static const char PROOF_SYSTEM_INFO[17] = "RISC0_STARK:v1__";
 static Digest hash_protocol_info(const uint8_t* info) {
   uint32_t e[16];
@@ -151,12 +168,17 @@ struct zkb_prover {
   };
   TraceSlot slots[2];
   cudaStream_t copy_stream = nullptr;
+  bool own_copy_stream = false;
   int stage_idx = 0, prove_idx = 0;
   const cudaEvent_t* group_ready = nullptr;      // staged proof in progress: per-group upload events the commits wait on
 
   void stage_traces(int po2_, const void* const h_traces[3]) {
     ZKB_REQUIRE(po2_ >= 6 && po2_ + 2 <= MAX_PO2, "segment po2 out of range [6, 24]");
-    if (!copy_stream) ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    if (!copy_stream) {
+      static const bool priv = [] { const char* e = getenv("ZKB_COPY_STREAM"); return e && !strcmp(e, "private"); }();      // measurement knob: one stream per prover (round-1 behaviour)
+      if (priv) { ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking)); own_copy_stream = true; }
+      else copy_stream = shared_copy_stream(ctx->device);
+    }
     TraceSlot& sl = slots[stage_idx];
     ZKB_REQUIRE(!sl.full, "both staging slots are full: call zkb_prove_staged first");
     if (!sl.consumed) {
@@ -201,7 +223,8 @@ struct zkb_prover {
       if (sl.consumed) cudaEventDestroy(sl.consumed);
       sl = TraceSlot();
     }
-    if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
+    if (copy_stream && own_copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr; own_copy_stream = false;      // the shared per-device stream is not ours to destroy
   }
 
   void reset() {

@@ -19,6 +19,26 @@ def owner_of(segment, world):
     return segment % world
 
 
+class SharedSegmentQueue:
+    """The segments of one session handed out across ALL ranks in arrival order: `take()` returns the next unclaimed segment index, or
+    None when the session is exhausted.  An atomic counter in torch.distributed's key-value store (the rendezvous store every process
+    group already has) -- no collective, no data between ranks.  For boxes where the ranks are not equally fast end to end (on this
+    pool GPUs 0-3 get 23 GB/s of host->device bandwidth and GPUs 4-7 35 GB/s when all eight upload): a static i mod N split waits for
+    the slowest rank, a queue lets it take fewer segments.  `take()` may be called from several threads of a rank."""
+
+    def __init__(self, n_segments, name, store=None):
+        import threading
+        if store is None:
+            import torch.distributed as dist
+            store = dist.distributed_c10d._get_default_store()
+        self.n, self.key, self.store, self.lock = int(n_segments), f"zkb200/queue/{name}", store, threading.Lock()
+
+    def take(self):
+        with self.lock:
+            i = int(self.store.add(self.key, 1)) - 1
+        return i if i < self.n else None
+
+
 def gather_results(local, n_segments, rank, world, dist=None):
     """local: {segment index: uint32 array (seal or digest)} proven by this rank.  Returns the full list in segment order
     on every rank (all_gather_object over the process group; plain dict merge when world == 1)."""
