@@ -122,3 +122,101 @@ def test_gpu_seal_verifies(shape, po2):
     with pytest.raises(ZkbError):
         verify_segment(blob, bad, cid)
     gp.close(); hal.close()
+
+
+def _fib_circuit():
+    """A satisfiable circuit OUTSIDE the SYN family: registers of three taps (back 0, 1, 2) and a gated linear recurrence
+         sel[i] * (d_j[i] - d_j[i-1] - k[i] * d_j[i-2]) == 0,   acc[i] = mix_0 * d_0[i] + d_1[i-2] on live rows
+    so that the verifier's per-register interpolation (three points), the three divisions of the {0,1,2} combo and the DEEP relation
+    are exercised by a seal that must VERIFY, not merely equal another prover's."""
+    from zktls_b200.circuit import CircuitBuilder, GROUP_ACCUM, GROUP_CODE, GROUP_DATA, GLOBAL_MIX
+    b = CircuitBuilder(1, 2, 3, 1, 1, info=b"FIB3:v1_________")
+    b.add_tap(GROUP_ACCUM, 0, 0)
+    for c in range(2):
+        b.add_tap(GROUP_CODE, c, 0)
+    for c in range(3):
+        for k in (0, 1, 2):
+            b.add_tap(GROUP_DATA, c, k)
+    b.finish_taps()
+    sel, kk = b.get(GROUP_CODE, 0, 0), b.get(GROUP_CODE, 1, 0)
+    top = b.and_eqz(b.true(), b.mul(sel, b.sub(sel, b.const(1))))
+    inner = b.true()
+    for j in range(3):
+        d0, d1, d2 = (b.get(GROUP_DATA, j, k) for k in (0, 1, 2))
+        inner = b.and_eqz(inner, b.sub(b.sub(d0, d1), b.mul(kk, d2)))
+    m0 = b.get_global(GLOBAL_MIX, 0)
+    inner = b.and_eqz(inner, b.sub(b.sub(b.get(GROUP_ACCUM, 0, 0), b.mul(m0, b.get(GROUP_DATA, 0, 0))), b.get(GROUP_DATA, 1, 2)))
+    b.ret = b.and_cond(top, sel, inner)
+    # the witness program of the accum column (device-side accumulate)
+    v = b.w_add(b.w_mul(b.w_get_global(GLOBAL_MIX, 0), b.w_get(GROUP_DATA, 0, 0)), b.w_get(GROUP_DATA, 1, 2))
+    b.w_set(0, v, b.w_get(GROUP_CODE, 0, 0))
+    return b
+
+
+def _fib_trace(po2, seed):
+    from zktls_b200.circuit import ZK_ROWS
+    P = 2013265921
+    n = 1 << po2
+    rng = np.random.default_rng(seed)
+    code = rng.integers(0, P, size=(2, n), dtype=np.uint64)
+    sel = np.zeros(n, np.uint64); sel[2: n - ZK_ROWS] = 1
+    code[0] = sel
+    data = rng.integers(0, P, size=(3, n), dtype=np.uint64)
+    for i in range(2, n - ZK_ROWS):
+        data[:, i] = (data[:, i - 1] + code[1, i] * data[:, i - 2] % P) % P
+    io = synth.encode(rng.integers(0, P, size=1, dtype=np.uint64)).astype(np.uint32)
+    return io, code, data
+
+
+def _fib_accum(po2, seed, code, data, mix_mont):
+    P = 2013265921
+    n = 1 << po2
+    m0 = int(synth.decode(mix_mont)[0])
+    acc = np.random.default_rng(seed + 1).integers(0, P, size=(1, n), dtype=np.uint64)
+    live = code[0].astype(bool)
+    v = (m0 * data[0] % P + np.roll(data[1], 2)) % P
+    acc[0][live] = v[live]
+    return acc
+
+
+@pytest.mark.parametrize("po2", [8, 10])
+def test_three_tap_registers_prove_and_verify_on_the_oracle(oracle, po2):
+    b = _fib_circuit(); blob = b.blob()
+    io, code, data = _fib_trace(po2, 40 + po2)
+    code_m, data_m = synth.to_mont(code), synth.to_mont(data)
+    pr = oracle.Prover(blob)
+    mix = pr.begin(po2, io, code_m, data_m)
+    acc = _fib_accum(po2, 40 + po2, code, data, mix)
+    assert np.array_equal(oracle.accumulate(blob, synth.to_mont(np.random.default_rng(41 + po2).integers(0, 2013265921, size=(1, 1 << po2), dtype=np.uint64)),
+                                            code_m, data_m, mix, io, po2), synth.to_mont(acc))          # the witness program computes the same column
+    seal = pr.finish(synth.to_mont(acc))
+    cid = control_id(po2, pr.roots()[0])
+    verify_segment(blob, seal, cid)
+    # one broken recurrence row -> the DEEP relation fails
+    bad = data.copy(); bad[1, 77] = (bad[1, 77] + 1) % 2013265921
+    pr2 = oracle.Prover(blob)
+    pr2.begin(po2, io, code_m, synth.to_mont(bad))
+    with pytest.raises(ZkbError, match="constraint polynomial"):
+        verify_segment(blob, pr2.finish(synth.to_mont(acc)), cid)
+
+
+@pytest.mark.gpu
+def test_three_tap_registers_prove_and_verify_on_the_gpu(oracle):
+    from zktls_b200.hal import B200Hal
+    from zktls_b200.prover import SegmentProver
+    hal = B200Hal(0)
+    b = _fib_circuit(); blob = b.blob(); po2 = 11
+    io, code, data = _fib_trace(po2, 7)
+    code_m, data_m = synth.to_mont(code), synth.to_mont(data)
+    gp = SegmentProver(hal, blob)
+    d_code, d_data = hal.copy_from_elem(code_m), hal.copy_from_elem(data_m)
+    mix = gp.begin(po2, io, d_code, d_data)
+    d_acc = hal.copy_from_elem(synth.to_mont(np.random.default_rng(8).integers(0, 2013265921, size=(1, 1 << po2), dtype=np.uint64)))
+    hal.accumulate(blob, d_acc, d_code, d_data, mix, io, po2)           # accum never visits the host
+    assert np.array_equal(d_acc.to_numpy(), synth.to_mont(_fib_accum(po2, 7, code, data, mix)))
+    seal = gp.finish(d_acc)
+    verify_segment(blob, seal, control_id(po2, gp.roots()[0]))
+    op = oracle.Prover(blob)
+    op.begin(po2, io, code_m, data_m)
+    assert np.array_equal(seal, op.finish(d_acc.to_numpy()))
+    gp.close(); hal.close()
