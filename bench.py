@@ -167,23 +167,6 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def pin_rank_to_gpu_numa_node(index):
-    """Best effort: run this rank's host threads (and so first-touch its pinned trace buffers) on the CPUs NVML reports as
-    local to its GPU, so that with 8 ranks the 8 x 1.17 GB uploads per step do not all cross one socket's memory controller."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-    except Exception:       # noqa: BLE001
-        pass
-
-
 def workload_config(po2=PO2):
     """identical in both arms (the driver compares the two `config` objects)"""
     name = "syn280-segment-po2-20" if po2 == PO2 else f"DEBUG po2={po2} (not the benchmark config)"
@@ -226,7 +209,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    pin_rank_to_gpu_numa_node(local_rank)
+    from zktls_b200.shard import bind_rank_to_gpu_numa_node
+    numa = bind_rank_to_gpu_numa_node(local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION from the environment or from
         # /etc/nccl.conf) is printed to stdout when the first communicator is created, so (i) ask for WARN unless the user
@@ -331,10 +315,14 @@ def main():
         for ev in first_up:
             ev.wait()
         while have:
+            ta = time.time()
             nxt = queue.take()
             if nxt:
                 provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
+            tb = time.time()
             s = provers[w].prove_staged(io)
+            if timeline is not None:
+                timeline.append((w, round((ta - timeline_t0[0]) * 1e3, 2), round((tb - timeline_t0[0]) * 1e3, 2), round((time.time() - timeline_t0[0]) * 1e3, 2)))
             have = nxt
         return s
 
@@ -352,6 +340,9 @@ def main():
         return out
 
     first_up = [threading.Event() for _ in range(inflight)]
+    # ZKB_BENCH_TIMELINE=<prefix>: every rank writes <prefix>_rank<r>.json with (worker, take, prove start, prove end) in ms per segment of
+    # the end-to-end arm and of the session (diagnostic; list.append is the only work added to the timed region)
+    timeline, timeline_t0, timelines = ([] if os.environ.get("ZKB_BENCH_TIMELINE") else None), [0.0], {}
 
     # ---- device-resident arm -----------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank); sampler.start()
@@ -378,9 +369,13 @@ def main():
     seal_h = run_host(min(args.warmup, 2) * inflight)
     barrier()
     first_up = [threading.Event() for _ in range(inflight)]
+    if timeline is not None:
+        timeline.clear(); timeline_t0[0] = time.time()
     hal.timer_start()
     seal_h = run_host(args.steps)
     ms_e2e = hal.timer_stop()
+    if timeline is not None:
+        timelines["e2e"] = sorted(timeline, key=lambda r: r[1])
     barrier()
     t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
     e2e_per_rank = [ms_e2e]
@@ -390,6 +385,10 @@ def main():
         e2e_per_rank = [float(x.item()) for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / (float(t.item()) / 1000.0)
+    numa_all = [numa]
+    if world > 1:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
     assert np.array_equal(seal, seal_h), "device-resident and host-buffer paths disagree"
 
     # ---- BASELINE metric "e2e TLS prove s": one TLS session = S continuation segments (S = 64 for a
@@ -407,14 +406,22 @@ def main():
                 sq = None
         barrier()
         hal.timer_start(); ts0 = time.time()
+        if timeline is not None:
+            timeline.clear(); timeline_t0[0] = time.time()
         run_host(mine, sq)
         ms_sess = hal.timer_stop()
+        if timeline is not None:
+            timelines["session"] = sorted(timeline, key=lambda r: r[1])
         barrier()
         t = torch.tensor([ms_sess], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         session = {"segments": args.session_segments, "seconds": float(t.item()) / 1000.0, "wall_s_rank0": time.time() - ts0, "sharing": sharing,
                    "what": "synthetic stand-in for one recorded TLS session: S independent SYN-280 2^20-cycle segments, segment-parallel over the ranks, host traces in / seals out"}
+
+    if timeline is not None:
+        with open(f"{os.environ['ZKB_BENCH_TIMELINE']}_rank{rank}.json", "w") as f:
+            json.dump({"rank": rank, "columns": ["worker", "take_ms", "prove_start_ms", "prove_end_ms"], **timelines}, f)
 
     # ---- roofline of the dominant kernel (hash_rows over the data group's LDE matrix), live CUDA events -----------------
     roof = None
@@ -514,7 +521,8 @@ def main():
                 "config": workload_config(po2), "segments_in_flight_per_gpu": inflight, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k",
-                        "per_rank_ms_per_step": [round(x / args.steps, 3) for x in e2e_per_rank]},
+                        "per_rank_ms_per_step": [round(x / args.steps, 3) for x in e2e_per_rank],
+                        "host_numa_binding_per_rank": numa_all},
                 "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if heavy:
             line["config"]["workload"] = "SECONDARY synheavy280-segment-po2-20: the benchmark segment's shape (280 columns, 2^20 cycles, Trace A) under the SYN-HEAVY " \

@@ -2,10 +2,15 @@
 whose every segment uploads 1.17 GB.  Each rank copies its own pinned buffer to its GPU `reps` times between two barriers;
 rank 0 prints per-rank and aggregate GB/s.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 tools/h2d_probe.py"""
-import os, time, json
+import os, sys, time, json
 import torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
+bound = None
+if "--bind" in sys.argv:        # run (and first-touch the pinned buffer) on the CPUs local to this rank's GPU, as bench.py does
+    from zktls_b200.shard import bind_rank_to_gpu_numa_node
+    bound = bind_rank_to_gpu_numa_node(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 nbytes = 1174405120          # one SYN-280 2^20 segment's three trace groups
@@ -36,5 +41,5 @@ for concurrent in (False, True):
     else: allg = [t]
     if rank == 0:
         per = [float(x.item()) for x in allg]
-        print(json.dumps({"ranks": world, "three_streams": concurrent, "per_rank_GBps": [round(x, 1) for x in per], "aggregate_GBps": round(sum(per), 1)}), flush=True)
+        print(json.dumps({"ranks": world, "bound": bound, "three_streams": concurrent, "per_rank_GBps": [round(x, 1) for x in per], "aggregate_GBps": round(sum(per), 1)}), flush=True)
 if world > 1: dist.destroy_process_group()

@@ -5,6 +5,7 @@ The reference proves a session's continuation segments one after another inside 
 segment i goes to rank i mod G (one process per GPU) and there is NO collective on the data path.  The only exchange is
 the gather of the results (seal + roots, ~0.27 MB per segment) for the recursion stage / the caller.
 """
+import os
 import numpy as np
 
 
@@ -17,6 +18,53 @@ def segments_for_rank(n_segments, rank, world):
 
 def owner_of(segment, world):
     return segment % world
+
+
+def gpu_numa_node(index):
+    """NUMA node of GPU `index` (NVML's PCI bus id -> /sys/bus/pci/devices/<bdf>/numa_node), or None when the platform does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        for name in (bus.lower(), bus.lower()[4:] if len(bus) > 12 else bus.lower()):      # NVML pads the domain to 8 hex digits
+            path = f"/sys/bus/pci/devices/{name}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+                return node if node >= 0 else None
+    except Exception:       # noqa: BLE001
+        pass
+    return None
+
+
+def bind_rank_to_gpu_numa_node(index):
+    """Best effort: run this rank's host threads on the CPUs of its GPU's NUMA node, so that the pinned trace buffers it allocates
+    afterwards are first-touched there and the 1.17 GB upload of every segment does not cross the socket interconnect.  Tries the
+    node's cpulist from sysfs first, NVML's affinity mask second.  Returns {"node", "cpus"} describing what was applied (cpus = 0:
+    nothing was changed)."""
+    cpus, node = set(), gpu_numa_node(index)
+    try:
+        if node is not None:
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus |= set(range(int(lo), int(hi or lo) + 1))
+    except Exception:       # noqa: BLE001
+        cpus = set()
+    if not cpus:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        except Exception:   # noqa: BLE001
+            cpus = set()
+    try:
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:       # noqa: BLE001
+        cpus = set()
+    return {"node": node, "cpus": len(cpus)}
 
 
 class SharedSegmentQueue:
