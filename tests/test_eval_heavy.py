@@ -99,6 +99,22 @@ def test_flat_form_matches_oracle_on_a_reduced_heavy_circuit(hal, oracle, po2, e
     assert np.array_equal(got, want)
 
 
+LONG_RUNS = dict(accum_cols=6, code_cols=6, data_cols=12, mix_size=5, out_size=4, majors=2, fanout=(1, 2, 2), leaf_constraints=72)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"ZKB_EC_UNROLL": "2"}, {"ZKB_EC_UNROLL": "4"}, {"ZKB_EC_UNROLL": "6"}, {}, {"ZKB_EC_PURE_LOADS": "1"},
+                                 {"ZKB_EC_UNROLL": "4", "ZKB_EC_PURE_LOADS": "1", "ZKB_EC_FLAT_GROUPS": "6", "ZKB_EC_UNIT": "128", "ZKB_EC_UNIT_VECS": "320"}])
+def test_compact_form_main_loops_and_tails(hal, oracle, env, monkeypatch):
+    """groups of 72 constraints give runs of one shape longer than any unroll factor of the compact form's main loop, so the unrolled
+    trips, the pair loop behind them and the odd last term all execute (the REDUCED circuit's runs are shorter than 8)"""
+    monkeypatch.setenv("ZKB_EC_FORM", "compact")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got, want = _eval_both(hal, oracle, circuit.syn_heavy_circuit(**LONG_RUNS), 7, 4242)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("form", ["compact", "flat"])
 def test_flat_form_agrees_with_the_other_forms_on_syn280(hal, oracle, form, monkeypatch):

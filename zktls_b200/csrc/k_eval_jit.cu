@@ -908,7 +908,18 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
   o << "#define ZKB_ALU_ADDS " << (env_u32("ZKB_EC_ALU_ADDS", 1, 0, 1) ? 1 : 0) << "\n" << PREAMBLE;
   o << "#define HALO " << halo << "u\n#define BLOCK " << points << "u\n#define ROWP " << rowp << "u\n" << PREAMBLE_STAGED;
   o << "typedef u64 ACC;\n#define GL(i) __ldg(gl + (i))\n";
-  o << "__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n#define TAP(o) lds32(spb + (o))\n";
+  // ZKB_EC_PURE_LOADS=1: record / power loads are plain (schedulable) asm; they cannot be hoisted over the staging barrier or merged
+  // across units because their base addresses are OUTPUTS of the volatile barrier statement.  0 (default): volatile loads in program
+  // order -- measured equal (profiles/r2_s_ec_compact_sweep.txt), and ptxas spends fewer IMAD.MOV on it.
+  const bool pure_loads = env_u32("ZKB_EC_PURE_LOADS", 0, 0, 1) != 0;
+  o << "#define LDR_VOL " << (pure_loads ? "" : "volatile") << "\n";
+  // operand records, powers and taps are read through 32-bit shared-window addresses (no 64-bit pointer arithmetic: IMAD.X / IADD3.X);
+  // the record / power loads are volatile because their staging area is rewritten per unit (a pure asm would be CSE'd across units);
+  // a tap address is spb + offset as min(a + b, ONES): one ALU-pipe VIADDMNMX instead of an IMAD.IADD on the multiplier pipe
+  o << "__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n"
+       "__device__ __forceinline__ u32 ldr32(u32 a) { u32 v; asm LDR_VOL(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n"
+       "__device__ __forceinline__ uint4 ldr128(u32 a) { uint4 v; asm LDR_VOL(\"ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\" : \"=r\"(v.x), \"=r\"(v.y), \"=r\"(v.z), \"=r\"(v.w) : \"r\"(a)); return v; }\n"
+       "#define TAP(o) lds32(ADD2(spb, (o)))\n";
   o << "#define FIX4 { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); }\n";
   o << "#define L(i) ((i) < 4 ? (&a0.x)[(i)] : (i) < 8 ? (&a1.x)[(i) - 4] : (i) < 12 ? (&a2.x)[(i) - 8] : (&a3.x)[(i) - 12])\n";
   o << "__device__ const uint4 zkb_units[" << urecs.size() << "] = {";
@@ -935,28 +946,33 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
        "    asm volatile(\"bar.sync %0, " << points << ";\" :: \"r\"(grp + 1u) : \"memory\");          // the group is done with the previous unit's records\n"
        "    for (u32 i = pt; i < ur.y; i += BLOCK) dsm[i] = zkb_prog[ur.x + i];\n"
        "    for (u32 i = pt; i < ur.w; i += BLOCK) wsm[i] = __ldg(pw + ur.z + i);\n"
-       "    asm volatile(\"bar.sync %0, " << points << ";\" :: \"r\"(grp + 1u) : \"memory\");\n"
-       "    const uint4* d = dsm; const uint4* w = wsm;\n"
-       "    const u32 n_groups = d->x; ++d;\n"
+       "    u32 d, w;          // defined by the barrier statement: loads through them stay behind it\n"
+       "    asm volatile(\"bar.sync %2, " << points << "; mov.u32 %0, %3; mov.u32 %1, %4;\" : \"=r\"(d), \"=r\"(w) : \"r\"(grp + 1u), \"r\"(saddr(dsm)), \"r\"(saddr(wsm)) : \"memory\");\n"
+       "    const u32 n_groups = ldr32(d); d += 16u;\n"
        "    for (u32 g = 0; g < n_groups; ++g) {\n"
-       "      const u32 n_conds = d->x, n_runs = d->y; ++d;\n"
+       "      const uint4 gh = ldr128(d); d += 16u;\n"
+       "      const u32 n_conds = gh.x, n_runs = gh.y;\n"
        "      u32 cp = 0u;\n"
-       "      for (u32 q = 0; q < n_conds; ++q) { const u32 cv = TAP(reinterpret_cast<const u32*>(d)[q]); cp = q ? mul(cp, cv) : cv; }\n"
-       "      d += (n_conds + 3u) >> 2;\n"
+       "      for (u32 q = 0; q < n_conds; ++q) { const u32 cv = TAP(ldr32(d + 4u * q)); cp = q ? mul(cp, cv) : cv; }\n"
+       "      d += ((n_conds + 3u) >> 2) << 4;\n"
        "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0;\n"
        "      for (u32 r = 0; r < n_runs; ++r) {\n"
-       "        const u32 shape = d->x, count = d->y; ++d;\n"
+       "        const uint4 rh = ldr128(d); d += 16u;\n"
+       "        const u32 shape = rh.x, count = rh.y;\n"
        "        switch (shape) {\n";
+  const uint32_t unroll = env_u32("ZKB_EC_UNROLL", 8, 2, 8) & ~1u;          // terms per trip of a shape's main loop (even)
   for (size_t sidx = 0; sidx < shapes.size(); ++sidx) {
     const uint32_t v = vecs_of(shapes[sidx].leaves);
     // one term: operands -> value -> four unreduced accumulations; terms are taken in PAIRS with one high-word fix per pair (the accumulators
     // tolerate two products between fixes), an odd last term gets its own -- no per-term parity test, no predicated fixes
     std::ostringstream term;
-    term << "{ const uint4 a0 = d[0]";
-    for (uint32_t q = 1; q < 4; ++q) term << ", a" << q << " = " << (q < v ? "d[" + std::to_string(q) + "]" : std::string("a0"));
-    term << "; d += " << v << "; const u32 v = " << shapes[sidx].expr << "; const uint4 m = *w++; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w); }";
-    o << "          case " << sidx << ": {\n            u32 i = 0;\n            for (; i + 2u <= count; i += 2u) {\n              " << term.str() << "\n              " << term.str()
-      << "\n              FIX4\n            }\n            if (i < count) {\n              " << term.str() << "\n              FIX4\n            }\n          } break;\n";
+    term << "{ const uint4 a0 = ldr128(d)";
+    for (uint32_t q = 1; q < 4; ++q) term << ", a" << q << " = " << (q < v ? "ldr128(d + " + std::to_string(16 * q) + "u)" : std::string("a0"));
+    term << "; d += " << 16 * v << "u; const u32 v = " << shapes[sidx].expr << "; const uint4 m = ldr128(w); w += 16u; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w); }";
+    const std::string pair = "              " + term.str() + "\n              " + term.str() + "\n              FIX4\n";
+    o << "          case " << sidx << ": {\n            u32 i = 0;\n";
+    if (unroll > 2) { o << "            for (; i + " << unroll << "u <= count; i += " << unroll << "u) {\n"; for (uint32_t q = 0; q < unroll; q += 2) o << pair; o << "            }\n"; }
+    o << "            for (; i + 2u <= count; i += 2u) {\n" << pair << "            }\n            if (i < count) {\n              " << term.str() << "\n              FIX4\n            }\n          } break;\n";
   }
   o << "        }\n      }\n"
        "      const u32 la = fin(A0), lb = fin(A1), lc = fin(A2), ld = fin(A3);\n"
