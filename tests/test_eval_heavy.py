@@ -104,10 +104,13 @@ LONG_RUNS = dict(accum_cols=6, code_cols=6, data_cols=12, mix_size=5, out_size=4
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"ZKB_EC_UNROLL": "2"}, {"ZKB_EC_UNROLL": "4"}, {"ZKB_EC_UNROLL": "6"}, {}, {"ZKB_EC_PURE_LOADS": "1"},
+                                 {"ZKB_EC_PPT": "1"}, {"ZKB_EC_PPT": "1", "ZKB_EC_UNROLL": "4"}, {"ZKB_EC_PPT": "1", "ZKB_EC_UNROLL": "2"},
+                                 {"ZKB_EC_FLAT_POINTS": "32"}, {"ZKB_EC_FLAT_POINTS": "64", "ZKB_EC_UNROLL": "4"},
                                  {"ZKB_EC_UNROLL": "4", "ZKB_EC_PURE_LOADS": "1", "ZKB_EC_FLAT_GROUPS": "6", "ZKB_EC_UNIT": "128", "ZKB_EC_UNIT_VECS": "320"}])
 def test_compact_form_main_loops_and_tails(hal, oracle, env, monkeypatch):
     """groups of 72 constraints give runs of one shape longer than any unroll factor of the compact form's main loop, so the unrolled
-    trips, the pair loop behind them and the odd last term all execute (the REDUCED circuit's runs are shorter than 8)"""
+    trips, the pair loop behind them and the odd last term all execute (the REDUCED circuit's runs are shorter than 8); with one and
+    with two points per thread (ZKB_EC_PPT; a 32-point tile falls back to one)"""
     monkeypatch.setenv("ZKB_EC_FORM", "compact")
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -74,9 +74,32 @@ Api& api() {
   static Api a;
   static std::once_flag once;
   std::call_once(once, [] {
-    void* rt = nullptr;
-    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) { rt = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (rt) break; }
+    // The NEWEST loadable NVRTC wins, not the first one found: a process that imported torch already has torch's bundled libnvrtc
+    // (12.8 here) mapped under the same SONAME, and its code for the compact eval_check form is 8 % slower than the toolkit's 12.9
+    // (134 vs 124 ms on SYN-HEAVY, profiles/r2_y_nvrtc_version.txt) -- the same source ran at two speeds depending on import order.
+    // Candidates by path are separate mappings (RTLD_LOCAL: no symbol interposition between two NVRTCs).  ZKB_NVRTC_LIB pins one.
+    void* rt = nullptr; int rt_ver = -1; std::string rt_dir;
+    {
+      std::vector<std::string> cands;
+      if (const char* pin = getenv("ZKB_NVRTC_LIB")) cands.push_back(pin);
+      else {
+        for (const char* var : {"CUDA_HOME", "CUDA_PATH"}) if (const char* h = getenv(var)) if (*h == '/') cands.push_back(std::string(h) + "/lib64/libnvrtc.so.12");
+        cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12"); cands.push_back("libnvrtc.so.12"); cands.push_back("libnvrtc.so");
+      }
+      for (const std::string& name : cands) {
+        void* h = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) continue;
+        int maj = 0, min = 0;
+        auto ver = (decltype(&nvrtcVersion))dlsym(h, "nvrtcVersion");
+        if (ver && ver(&maj, &min) == NVRTC_SUCCESS && maj * 100 + min > rt_ver) {
+          rt = h; rt_ver = maj * 100 + min;
+          Dl_info info; rt_dir.clear();
+          if (dladdr((void*)ver, &info) && info.dli_fname) { std::string f = info.dli_fname; size_t sl = f.rfind('/'); if (sl != std::string::npos) rt_dir = f.substr(0, sl); }
+        }
+      }
+    }
     if (!rt) { a.why = "libnvrtc.so.12 not loadable"; return; }
+    if (getenv("ZKB_EC_VERBOSE")) fprintf(stderr, "zkb200: NVRTC %d.%d from %s\n", rt_ver / 100, rt_ver % 100, rt_dir.empty() ? "?" : rt_dir.c_str());
     bool all = true;
     auto sym = [&](void* lib, const char* n) { void* p = dlsym(lib, n); if (!p) { all = false; a.why = std::string("missing symbol ") + n; } return p; };
     a.createProgram = (decltype(a.createProgram))sym(rt, "nvrtcCreateProgram");
@@ -91,8 +114,11 @@ Api& api() {
     a.getPTX = (decltype(a.getPTX))dlsym(rt, "nvrtcGetPTX");
     a.ok = all;
     {
-      void* jl = nullptr;
-      for (const char* name : {"libnvJitLink.so.12", "libnvJitLink.so", "/usr/local/cuda/lib64/libnvJitLink.so.12"}) { jl = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (jl) break; }
+      void* jl = nullptr;          // the nvJitLink that ships next to the chosen NVRTC first (same toolkit version: it must accept that NVRTC's PTX)
+      std::vector<std::string> jcands;
+      if (!rt_dir.empty()) jcands.push_back(rt_dir + "/libnvJitLink.so.12");
+      jcands.push_back("libnvJitLink.so.12"); jcands.push_back("libnvJitLink.so"); jcands.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
+      for (const std::string& name : jcands) { jl = dlopen(name.c_str(), RTLD_NOW | RTLD_LOCAL); if (jl) break; }
       if (!jl) a.jl_why = "libnvJitLink.so.12 not loadable";
       else {
         auto vsym = [&](const char* base) -> void* {
@@ -787,7 +813,7 @@ static bool generate_flat(const CircuitDef& c, GenInfo& gi, FlatProgram& prog) {
 //   runs...; run = [shape, count, 0, 0] terms...; term = ceil(leaves / 4) granules of operands in depth-first order.
 // Applies when every AndCond condition is a plain tap and no expression has more than 16 leaves; otherwise the PTX flat form is used.
 struct CompactShape { std::string expr; uint32_t leaves = 0; };
-static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src) {
+static bool generate_compact_ppt(const CircuitDef& c, GenInfo& gi, std::string& src, const uint32_t ppt) {
   const size_t n = c.steps.size();
   std::vector<size_t> fp_step(c.n_fp_vars), mx_step(c.n_mix_vars);
   { uint32_t fi = 0, mi = 0; for (size_t i = 0; i < n; ++i) { if (c.steps[i].op <= PX_MUL) fp_step[fi++] = i; else mx_step[mi++] = i; } }
@@ -823,9 +849,14 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
   uint32_t halo = 0;
   for (const TapDef& t : c.taps) { slot.emplace(std::make_pair(t.group, t.column), 0u); halo = std::max(halo, 4 * t.back); }
   { uint32_t k = 0; for (auto& kv : slot) kv.second = k++; }
-  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", 4, 1, 8);
-  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", 256, 8, 512);
-  const uint32_t unit_vecs = env_u32("ZKB_EC_UNIT_VECS", 640, 64, 4096);          // operand-table granules (16 B) a unit may use
+  // points per thread: with 2, a thread evaluates rows pt and pt + T of the tile (T = threads per warp group): one operand record, one
+  // power load and one tap-address addition serve two points (the second tap is the same LDS with an immediate offset), and there are
+  // twice as many independent chains per warp.  The block keeps 512 threads as 8 groups of 64, with correspondingly smaller units.
+  // Measured on SYN-HEAVY (profiles/r2_v_ec_ppt_sweep.txt): 135.4 ms with one point per thread (main loop of 8 terms), 123.6 ms with two
+  // (pairs of terms); ZKB_EC_PPT=1 restores the former.
+  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", ppt == 2 ? 8 : 4, 1, 8);
+  const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", ppt == 2 ? 96 : 256, 8, 512);
+  const uint32_t unit_vecs = env_u32("ZKB_EC_UNIT_VECS", ppt == 2 ? 240 : 640, 64, 4096);          // operand-table granules (16 B) a unit may use
   uint32_t points = env_u32("ZKB_EC_FLAT_POINTS", 128, 32, 512);
   const size_t stage_words = (size_t)groups * ((size_t)unit_terms + unit_vecs) * 4;
   while (points > 32 && ((size_t)slot.size() * (points + halo) * 4 + (size_t)(groups - 1) * points * 16 + stage_words * 4 + 64 > 220 * 1024)) points >>= 1;
@@ -864,7 +895,9 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
   gi.n_powers = (uint32_t)terms.size();
   gi.term_power.resize(terms.size());
   for (size_t t = 0; t < terms.size(); ++t) gi.term_power[t] = terms[t].power;
-  gi.block = (int)(points * groups); gi.points = (int)points; gi.staged = true;
+  const uint32_t tpg = points / ppt;                       // threads per warp group
+  if (tpg % 32) return false;
+  gi.block = (int)(tpg * groups); gi.points = (int)points; gi.staged = true;
   // the operand table, unit by unit
   std::vector<uint32_t> prog;                              // granules of 4 words
   struct UnitRec { uint32_t off, vecs, term0, nterms; };
@@ -920,7 +953,9 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
        "__device__ __forceinline__ u32 ldr32(u32 a) { u32 v; asm LDR_VOL(\"ld.shared.u32 %0, [%1];\" : \"=r\"(v) : \"r\"(a)); return v; }\n"
        "__device__ __forceinline__ uint4 ldr128(u32 a) { uint4 v; asm LDR_VOL(\"ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\" : \"=r\"(v.x), \"=r\"(v.y), \"=r\"(v.z), \"=r\"(v.w) : \"r\"(a)); return v; }\n"
        "#define TAP(o) lds32(ADD2(spb, (o)))\n";
-  o << "#define FIX4 { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); }\n";
+  if (ppt == 2) o << "__device__ __forceinline__ u32 lds32b(u32 a) { u32 v; asm(\"ld.shared.u32 %0, [%1+" << 4 * tpg << "];\" : \"=r\"(v) : \"r\"(a)); return v; }\n"
+                     "#define TAPB(o) lds32b(ADD2(spb, (o)))\n";
+  o << "#define FIX4 { A0 = fixhi(A0); A1 = fixhi(A1); A2 = fixhi(A2); A3 = fixhi(A3); " << (ppt == 2 ? "B0 = fixhi(B0); B1 = fixhi(B1); B2 = fixhi(B2); B3 = fixhi(B3); " : "") << "}\n";
   o << "#define L(i) ((i) < 4 ? (&a0.x)[(i)] : (i) < 8 ? (&a1.x)[(i) - 4] : (i) < 12 ? (&a2.x)[(i) - 8] : (&a3.x)[(i) - 12])\n";
   o << "__device__ const uint4 zkb_units[" << urecs.size() << "] = {";
   for (const UnitRec& u : urecs) o << "{" << u.off << "u," << u.vecs << "u," << u.term0 << "u," << u.nterms << "u},";
@@ -934,58 +969,82 @@ static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src)
        "  u32* const part = zkb_sm + " << col_words << "u;\n"
        "  uint4* const stage = reinterpret_cast<uint4*>(part + " << (size_t)(groups - 1) * points * 4 << "u);\n"
        "  u64* const full = reinterpret_cast<u64*>(part + " << (size_t)(groups - 1) * points * 4 + stage_words << "u);\n"
-       "  const u32 c0 = blockIdx.x * BLOCK, pt = threadIdx.x % BLOCK, grp = threadIdx.x / BLOCK;\n"
+       "  const u32 c0 = blockIdx.x * BLOCK, pt = threadIdx.x % " << tpg << "u, grp = threadIdx.x / " << tpg << "u;\n"
        "  uint4* const dsm = stage + grp * " << (unit_terms + unit_vecs) << "u;      // this warp group's operand records ...\n"
        "  uint4* const wsm = dsm + " << unit_vecs << "u;                              // ... and poly_mix powers of the unit it is running\n"
        "  if (threadIdx.x == 0) { mbar_init(full, 1u); asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\"); }\n  __syncthreads();\n"
        "  if (threadIdx.x == 0) {\n    mbar_expect_tx(full, " << col_words * 4 << "u);\n";
   for (auto& kv : slot) o << "    copy_col(zkb_sm + " << (size_t)kv.second * rowp << "u, g" << kv.first.first << " + (size_t)" << kv.first.second << " * dom, c0, mask, full);\n";
-  o << "  }\n  mbar_wait(full, 0u);\n  const u32 spb = saddr(zkb_sm + pt + HALO);          // shared-window byte address of this thread's row in column slot 0\n  u32 ra = 0u, rb = 0u, rc = 0u, rd = 0u;\n"
-       "  for (u32 u = grp; u < " << urecs.size() << "u; u += " << groups << "u) {\n"
+  const bool two = ppt == 2;
+  o << "  }\n  mbar_wait(full, 0u);\n  const u32 spb = saddr(zkb_sm + pt + HALO);          // shared-window byte address of this thread's row in column slot 0\n"
+       "  u32 ra = 0u, rb = 0u, rc = 0u, rd = 0u;\n" << (two ? "  u32 sa = 0u, sb = 0u, sc = 0u, sd = 0u;          // the second point (row pt + T)\n" : "")
+    << "  for (u32 u = grp; u < " << urecs.size() << "u; u += " << groups << "u) {\n"
        "    const uint4 ur = zkb_units[u];\n"
-       "    asm volatile(\"bar.sync %0, " << points << ";\" :: \"r\"(grp + 1u) : \"memory\");          // the group is done with the previous unit's records\n"
-       "    for (u32 i = pt; i < ur.y; i += BLOCK) dsm[i] = zkb_prog[ur.x + i];\n"
-       "    for (u32 i = pt; i < ur.w; i += BLOCK) wsm[i] = __ldg(pw + ur.z + i);\n"
+       "    asm volatile(\"bar.sync %0, " << tpg << ";\" :: \"r\"(grp + 1u) : \"memory\");          // the group is done with the previous unit's records\n"
+       "    for (u32 i = pt; i < ur.y; i += " << tpg << "u) dsm[i] = zkb_prog[ur.x + i];\n"
+       "    for (u32 i = pt; i < ur.w; i += " << tpg << "u) wsm[i] = __ldg(pw + ur.z + i);\n"
        "    u32 d, w;          // defined by the barrier statement: loads through them stay behind it\n"
-       "    asm volatile(\"bar.sync %2, " << points << "; mov.u32 %0, %3; mov.u32 %1, %4;\" : \"=r\"(d), \"=r\"(w) : \"r\"(grp + 1u), \"r\"(saddr(dsm)), \"r\"(saddr(wsm)) : \"memory\");\n"
+       "    asm volatile(\"bar.sync %2, " << tpg << "; mov.u32 %0, %3; mov.u32 %1, %4;\" : \"=r\"(d), \"=r\"(w) : \"r\"(grp + 1u), \"r\"(saddr(dsm)), \"r\"(saddr(wsm)) : \"memory\");\n"
        "    const u32 n_groups = ldr32(d); d += 16u;\n"
        "    for (u32 g = 0; g < n_groups; ++g) {\n"
        "      const uint4 gh = ldr128(d); d += 16u;\n"
        "      const u32 n_conds = gh.x, n_runs = gh.y;\n"
-       "      u32 cp = 0u;\n"
-       "      for (u32 q = 0; q < n_conds; ++q) { const u32 cv = TAP(ldr32(d + 4u * q)); cp = q ? mul(cp, cv) : cv; }\n"
+       "      u32 cp = 0u" << (two ? ", cq = 0u" : "") << ";\n"
+       "      for (u32 q = 0; q < n_conds; ++q) { const u32 co = ldr32(d + 4u * q); const u32 cv = TAP(co); cp = q ? mul(cp, cv) : cv;"
+    << (two ? " const u32 cw = TAPB(co); cq = q ? mul(cq, cw) : cw;" : "") << " }\n"
        "      d += ((n_conds + 3u) >> 2) << 4;\n"
-       "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0;\n"
+       "      ACC A0 = 0, A1 = 0, A2 = 0, A3 = 0" << (two ? ", B0 = 0, B1 = 0, B2 = 0, B3 = 0" : "") << ";\n"
        "      for (u32 r = 0; r < n_runs; ++r) {\n"
        "        const uint4 rh = ldr128(d); d += 16u;\n"
        "        const u32 shape = rh.x, count = rh.y;\n"
        "        switch (shape) {\n";
-  const uint32_t unroll = env_u32("ZKB_EC_UNROLL", 8, 2, 8) & ~1u;          // terms per trip of a shape's main loop (even)
+  const uint32_t unroll = env_u32("ZKB_EC_UNROLL", two ? 2 : 8, 2, 8) & ~1u;          // terms per trip of a shape's main loop (even)
   for (size_t sidx = 0; sidx < shapes.size(); ++sidx) {
     const uint32_t v = vecs_of(shapes[sidx].leaves);
     // one term: operands -> value -> four unreduced accumulations; terms are taken in PAIRS with one high-word fix per pair (the accumulators
     // tolerate two products between fixes), an odd last term gets its own -- no per-term parity test, no predicated fixes
+    std::string expr_b = shapes[sidx].expr;
+    for (size_t at = 0; (at = expr_b.find("TAP(", at)) != std::string::npos; at += 5) expr_b.replace(at, 4, "TAPB(");
     std::ostringstream term;
     term << "{ const uint4 a0 = ldr128(d)";
     for (uint32_t q = 1; q < 4; ++q) term << ", a" << q << " = " << (q < v ? "ldr128(d + " + std::to_string(16 * q) + "u)" : std::string("a0"));
-    term << "; d += " << 16 * v << "u; const u32 v = " << shapes[sidx].expr << "; const uint4 m = ldr128(w); w += 16u; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w); }";
+    term << "; d += " << 16 * v << "u; const u32 v = " << shapes[sidx].expr << "; " << (two ? "const u32 vb = " + expr_b + "; " : "")
+         << "const uint4 m = ldr128(w); w += 16u; wacc(A0, v, m.x); wacc(A1, v, m.y); wacc(A2, v, m.z); wacc(A3, v, m.w); "
+         << (two ? "wacc(B0, vb, m.x); wacc(B1, vb, m.y); wacc(B2, vb, m.z); wacc(B3, vb, m.w); " : "") << "}";
     const std::string pair = "              " + term.str() + "\n              " + term.str() + "\n              FIX4\n";
     o << "          case " << sidx << ": {\n            u32 i = 0;\n";
     if (unroll > 2) { o << "            for (; i + " << unroll << "u <= count; i += " << unroll << "u) {\n"; for (uint32_t q = 0; q < unroll; q += 2) o << pair; o << "            }\n"; }
     o << "            for (; i + 2u <= count; i += 2u) {\n" << pair << "            }\n            if (i < count) {\n              " << term.str() << "\n              FIX4\n            }\n          } break;\n";
   }
   o << "        }\n      }\n"
-       "      const u32 la = fin(A0), lb = fin(A1), lc = fin(A2), ld = fin(A3);\n"
-       "      if (n_conds) { ra = add(ra, mul(la, cp)); rb = add(rb, mul(lb, cp)); rc = add(rc, mul(lc, cp)); rd = add(rd, mul(ld, cp)); }\n"
-       "      else { ra = add(ra, la); rb = add(rb, lb); rc = add(rc, lc); rd = add(rd, ld); }\n"
-       "    }\n  }\n";
-  if (groups > 1) o << "  if (grp) { uint4* q = reinterpret_cast<uint4*>(part) + (grp - 1u) * BLOCK + pt; *q = make_uint4(ra, rb, rc, rd); }\n  __syncthreads();\n  if (grp) return;\n"
-                       "  for (u32 g = 0; g < " << groups - 1 << "u; ++g) { const uint4 q = reinterpret_cast<const uint4*>(part)[g * BLOCK + pt]; ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); }\n";
+       "      { const u32 la = fin(A0), lb = fin(A1), lc = fin(A2), ld = fin(A3);\n"
+       "        if (n_conds) { ra = add(ra, mul(la, cp)); rb = add(rb, mul(lb, cp)); rc = add(rc, mul(lc, cp)); rd = add(rd, mul(ld, cp)); }\n"
+       "        else { ra = add(ra, la); rb = add(rb, lb); rc = add(rc, lc); rd = add(rd, ld); } }\n";
+  if (two) o << "      { const u32 la = fin(B0), lb = fin(B1), lc = fin(B2), ld = fin(B3);\n"
+                "        if (n_conds) { sa = add(sa, mul(la, cq)); sb = add(sb, mul(lb, cq)); sc = add(sc, mul(lc, cq)); sd = add(sd, mul(ld, cq)); }\n"
+                "        else { sa = add(sa, la); sb = add(sb, lb); sc = add(sc, lc); sd = add(sd, ld); } }\n";
+  o << "    }\n  }\n";
+  if (groups > 1) {
+    o << "  if (grp) { uint4* q = reinterpret_cast<uint4*>(part) + (grp - 1u) * BLOCK + pt; *q = make_uint4(ra, rb, rc, rd); " << (two ? "q[" + std::to_string(tpg) + "] = make_uint4(sa, sb, sc, sd); " : "") << "}\n"
+         "  __syncthreads();\n  if (grp) return;\n"
+         "  for (u32 g = 0; g < " << groups - 1 << "u; ++g) { const uint4* qp = reinterpret_cast<const uint4*>(part) + g * BLOCK + pt; const uint4 q = *qp; ra = add(ra, q.x); rb = add(rb, q.y); rc = add(rc, q.z); rd = add(rd, q.w); "
+      << (two ? "const uint4 q2 = qp[" + std::to_string(tpg) + "]; sa = add(sa, q2.x); sb = add(sb, q2.y); sc = add(sc, q2.z); sd = add(sd, q2.w); " : "") << "}\n";
+  }
   o << "  const u32 c = c0 + pt;\n"
-       "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;\n"
-       "  st(check + c, mul(ra, den)); st(check + dom + c, mul(rb, den)); st(check + 2 * dom + c, mul(rc, den)); st(check + 3 * dom + c, mul(rd, den));\n}\n";
+       "  const u32 den = (c & 3u) == 0 ? invden.x : (c & 3u) == 1 ? invden.y : (c & 3u) == 2 ? invden.z : invden.w;          // (T is a multiple of 4: the same for both points)\n"
+       "  st(check + c, mul(ra, den)); st(check + dom + c, mul(rb, den)); st(check + 2 * dom + c, mul(rc, den)); st(check + 3 * dom + c, mul(rd, den));\n";
+  if (two) o << "  { const u32 c2 = c + " << tpg << "u; st(check + c2, mul(sa, den)); st(check + dom + c2, mul(sb, den)); st(check + 2 * dom + c2, mul(sc, den)); st(check + 3 * dom + c2, mul(sd, den)); }\n";
+  o << "}\n";
   src = o.str();
   return true;
+}
+static bool generate_compact(const CircuitDef& c, GenInfo& gi, std::string& src) {
+  const uint32_t ppt = env_u32("ZKB_EC_PPT", 2, 1, 2);
+  if (ppt == 2) {
+    GenInfo g2 = gi; std::string s2;
+    if (generate_compact_ppt(c, g2, s2, 2)) { gi = g2; src.swap(s2); return true; }          // (a tile narrower than 64 points leaves less than a warp per group)
+  }
+  return generate_compact_ppt(c, gi, src, 1);
 }
 static bool compact_wanted() { const char* e = getenv("ZKB_EC_FORM"); return !(e && !strcmp(e, "flat")); }      // ZKB_EC_FORM=flat forces the PTX flat form
 
