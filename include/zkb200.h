@@ -111,6 +111,10 @@ zkb_err zkb_eltwise_add_elem(zkb_ctx* ctx, void* d_out, const void* d_a, const v
 zkb_err zkb_eltwise_copy_elem(zkb_ctx* ctx, void* d_out, const void* d_in, size_t n);
 zkb_err zkb_eltwise_zeroize_elem(zkb_ctx* ctx, void* d_io, size_t n);
 zkb_err zkb_gather_sample(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t idx, size_t size, size_t stride);
+/* Batched gather_sample (SURVEY.md 8b "+ batched zkb_gather_rows"): the query phase of MerkleTreeProver::prove / fri_prove reads one
+ * row per query; row q of dst (size elements) = gather_sample(src, h_idx[q], size, stride), all n_idx <= 65535 rows in one launch
+ * instead of n_idx launches.  src_len = elements in src (every row is bounds-checked against it); h_idx is a host slice. */
+zkb_err zkb_gather_rows(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t src_len, const uint32_t* h_idx, size_t n_idx, size_t size, size_t stride);
 zkb_err zkb_prefix_products(zkb_ctx* ctx, void* d_io_fp4, size_t n);
 /* Hal::scatter(into, index, offsets, values) (witness-generation helper): for every row r < n_rows and k in
  * [h_index[r], h_index[r+1]): into[h_offsets[k]] = h_values[k].  index/offsets/values are host slices as in the trait;
@@ -137,8 +141,9 @@ zkb_err zkb_eval_check_precompile(const uint32_t* h_circuit, size_t circuit_word
 /* CircuitHal::accumulate(ctrl, io, data, mix, accum, steps) (risc0-circuit-rv32im `prove/hal/{cpu,cuda}.rs`, run by
  * prove_segment between the data commit and the accum commit; in-tree call site crates/guest-prover-r0/src/prover.rs:90):
  * fills the accum group's columns on the device from the code (= ctrl) and data traces, the `mix` globals that
- * zkb_prover_segment_begin returned, and io.  Rows the circuit leaves unconstrained keep the caller's contents.  The
- * witness program belongs to the circuit: built in for the SYN family, an error string for any other circuit info. */
+ * zkb_prover_segment_begin returned, and io.  Rows / columns the circuit's witness program does not write keep the caller's
+ * contents.  The witness program is DATA: the `n_wsteps` section of the circuit blob (W_CONST .. W_PREFIX_PRODUCT),
+ * JIT-compiled per phase; a circuit whose blob carries no witness program gets an error string. */
 zkb_err zkb_accumulate(zkb_ctx* ctx, const uint32_t* h_circuit, size_t circuit_words, void* d_accum, const void* d_code,
                        const void* d_data, const uint32_t* h_mix, const uint32_t* h_io, int po2);
 

@@ -48,6 +48,7 @@ extern "C" {
     pub fn zkb_eltwise_copy_elem(ctx: *mut ZkbCtx, d_out: *mut c_void, d_in: *const c_void, n: usize) -> ZkbErr;
     pub fn zkb_eltwise_zeroize_elem(ctx: *mut ZkbCtx, d_io: *mut c_void, n: usize) -> ZkbErr;
     pub fn zkb_gather_sample(ctx: *mut ZkbCtx, d_dst: *mut c_void, d_src: *const c_void, idx: usize, size: usize, stride: usize) -> ZkbErr;
+    pub fn zkb_gather_rows(ctx: *mut ZkbCtx, d_dst: *mut c_void, d_src: *const c_void, src_len: usize, h_idx: *const u32, n_idx: usize, size: usize, stride: usize) -> ZkbErr;
     pub fn zkb_prefix_products(ctx: *mut ZkbCtx, d_io_fp4: *mut c_void, n: usize) -> ZkbErr;
     pub fn zkb_scatter(ctx: *mut ZkbCtx, d_into: *mut c_void, into_len: usize, h_index: *const u32, n_rows: usize, h_offsets: *const u32, h_values: *const u32) -> ZkbErr;
     pub fn zkb_eval_check(ctx: *mut ZkbCtx, d_check: *mut c_void, h_circuit: *const u32, circuit_words: usize, d_accum: *const c_void, d_code: *const c_void, d_data: *const c_void, h_mix_g: *const u32, h_out_g: *const u32, h_poly_mix: *const u32, po2: c_int) -> ZkbErr;

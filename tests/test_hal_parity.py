@@ -189,6 +189,13 @@ def test_eltwise_misc(hal, oracle):
     g = hal.alloc_elem(50)
     hal.gather_sample(g, hal.copy_from_elem(a), 13, 50, 199)
     assert np.array_equal(g.to_numpy(), oracle.gather_sample(a, 13, 50, 199))
+    # batched form: one launch for all queries of a tree
+    idx = np.array([0, 13, 198, 57, 13], dtype=np.uint32)
+    gr = hal.alloc_elem(idx.size * 50)
+    hal.gather_rows(gr, hal.copy_from_elem(a), idx, 50, 199)
+    assert np.array_equal(gr.to_numpy(), np.concatenate([oracle.gather_sample(a, int(i), 50, 199) for i in idx]))
+    with pytest.raises(Exception, match="outside the source"):
+        hal.gather_rows(gr, hal.copy_from_elem(a), np.array([a.size - 10], dtype=np.uint32), 50, 199)
 
 
 @pytest.mark.parametrize("n", [1, 5, 64, 257, 5000, 1 << 15])

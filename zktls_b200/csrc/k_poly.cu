@@ -473,6 +473,16 @@ void fill_u32(zkb_ctx* ctx, uint32_t* x, size_t n, uint32_t v) {
   if (!n) return;
   k_fill<<<grid_for(n, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(x, n, v); launched(ctx);
 }
+// all queries of one tree in one launch: row q of dst = gather_sample(src, idx[q], size, stride)
+__global__ void k_gather_rows(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, size_t size, size_t stride) {
+  const size_t q = blockIdx.y, base = idx[q];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x) dst[q * size + i] = src[base + i * stride];
+}
+void gather_rows(zkb_ctx* ctx, uint32_t* dst, const uint32_t* src, const uint32_t* d_idx, size_t n_idx, size_t size, size_t stride) {
+  if (!size || !n_idx) return;
+  dim3 grid((unsigned)std::min<size_t>(grid_for(size, EW_BLOCK), 1024), (unsigned)n_idx);
+  k_gather_rows<<<grid, EW_BLOCK, 0, ctx->stream>>>(dst, src, d_idx, size, stride); launched(ctx);
+}
 void gather_sample(zkb_ctx* ctx, uint32_t* dst, const uint32_t* src, size_t idx, size_t size, size_t stride) {
   if (!size) return;
   k_gather<<<grid_for(size, EW_BLOCK), EW_BLOCK, 0, ctx->stream>>>(dst, src, idx, size, stride); launched(ctx);
@@ -606,6 +616,20 @@ zkb_err zkb_eltwise_zeroize_elem(zkb_ctx* ctx, void* d_io, size_t n) {
 }
 zkb_err zkb_gather_sample(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t idx, size_t size, size_t stride) {
   ZKB_API_BEGIN use(ctx); ZKB_REQUIRE((d_dst && d_src) || !size, "null buffer"); gather_sample(ctx, (uint32_t*)d_dst, (const uint32_t*)d_src, idx, size, stride); ZKB_API_END
+}
+zkb_err zkb_gather_rows(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t src_len, const uint32_t* h_idx, size_t n_idx, size_t size, size_t stride) {
+  ZKB_API_BEGIN use(ctx);
+  if (!n_idx || !size) return nullptr;
+  ZKB_REQUIRE(d_dst && d_src && h_idx, "null buffer");
+  ZKB_REQUIRE(n_idx <= 65535, "gather_rows: more than 65535 rows in one call");
+  for (size_t q = 0; q < n_idx; ++q) ZKB_REQUIRE((size_t)h_idx[q] + (size - 1) * stride < src_len, "gather_rows: a row reaches outside the source buffer");
+  uint32_t* d_idx = nullptr;
+  pool_alloc(ctx, &d_idx, n_idx * 4);
+  ZKB_CUDA(cudaMemcpyAsync(d_idx, h_idx, n_idx * 4, cudaMemcpyHostToDevice, ctx->stream));
+  gather_rows(ctx, (uint32_t*)d_dst, (const uint32_t*)d_src, d_idx, n_idx, size, stride);
+  ZKB_CUDA(cudaStreamSynchronize(ctx->stream));          // h_idx is the caller's (pageable) memory: done with it before returning
+  pool_free(ctx, d_idx);
+  ZKB_API_END
 }
 zkb_err zkb_scatter(zkb_ctx* ctx, void* d_into, size_t into_len, const uint32_t* h_index, size_t n_rows, const uint32_t* h_offsets, const uint32_t* h_values) {
   ZKB_API_BEGIN use(ctx);

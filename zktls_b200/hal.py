@@ -208,6 +208,11 @@ class B200Hal:
     def gather_sample(self, dst, src, idx, size, stride):
         check(lib().zkb_gather_sample(self.ctx, C.c_void_p(dst.ptr), C.c_void_p(src.ptr), _sz(idx), _sz(size), _sz(stride)))
 
+    def gather_rows(self, dst, src, idx, size, stride):
+        """dst[q * size + i] = src[idx[q] + i * stride]: every query's row of one tree in one launch (batched gather_sample)"""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        check(lib().zkb_gather_rows(self.ctx, C.c_void_p(dst.ptr), C.c_void_p(src.ptr), _sz(src.size), idx.ctypes.data_as(C.POINTER(C.c_uint32)), _sz(idx.size), _sz(size), _sz(stride)))
+
     def prefix_products(self, io):
         check(lib().zkb_prefix_products(self.ctx, C.c_void_p(io.ptr), _sz(io.size)))
 
