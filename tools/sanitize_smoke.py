@@ -18,6 +18,7 @@ for po2, count in ((4, 3), (10, 2), (13, 2), (16, 1)):
 pd = hal.copy_from_extelem(fp(4 * 5000)); hal.poly_divide(pd, fp(4)); hal.prefix_products(pd)
 xs = hal.copy_from_extelem(fp(4 * 5)); out = hal.alloc_extelem(5)
 hal.batch_evaluate_any(hal.copy_from_elem(fp(3 << 12)), 3, hal.copy_from_u32(np.array([0, 1, 2, 2, 0], np.uint32)), xs, out)
+src = hal.copy_from_elem(fp(4096)); gr = hal.alloc_elem(3 * 16); hal.gather_rows(gr, src, np.array([0, 7, 255], dtype=np.uint32), 16, 256)
 shape = dict(accum_cols=4, code_cols=3, data_cols=6, mix_size=5, out_size=4)
 blob = circuit.syn_circuit(**shape).blob()
 pr = SegmentProver(hal, blob)
