@@ -297,7 +297,7 @@ def main():
                 self.left -= 1
                 return True
 
-    def host_worker(w, queue):
+    def host_worker(w, queue, h_accum="host"):
         """Segments from HOST (pinned) buffers through the C-ABI, double-buffered: the 1.17 GB upload of the worker's next segment
         runs on the copy stream while the current one is proven.  Every segment's host->device copy and seal read-back happen
         inside this call.  A proof starts as soon as its 64 MB code group has landed (per-group upload events inside
@@ -309,8 +309,9 @@ def main():
         have = queue.take()
         if w > 0:
             first_up[w - 1].wait()
+        acc = h_np[2] if h_accum == "host" else None          # None: the accum group is computed on the device (CircuitHal::accumulate)
         if have:
-            provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
+            provers[w].stage(po2, h_np[0], h_np[1], acc)
         first_up[w].set()
         for ev in first_up:
             ev.wait()
@@ -318,7 +319,7 @@ def main():
             ta = time.time()
             nxt = queue.take()
             if nxt:
-                provers[w].stage(po2, h_np[0], h_np[1], h_np[2])
+                provers[w].stage(po2, h_np[0], h_np[1], acc)
             tb = time.time()
             s = provers[w].prove_staged(io)
             if timeline is not None:
@@ -334,9 +335,9 @@ def main():
         def take(self):
             return self.q.take() is not None
 
-    def run_host(k, queue=None):
+    def run_host(k, queue=None, h_accum="host"):
         q = queue or SegmentQueue(k)
-        out = run_workers(lambda w, _k: host_worker(w, q), inflight)       # one call per worker; the queue decides who proves what
+        out = run_workers(lambda w, _k: host_worker(w, q, h_accum), inflight)       # one call per worker; the queue decides who proves what
         return out
 
     first_up = [threading.Event() for _ in range(inflight)]
@@ -390,6 +391,28 @@ def main():
         numa_all = [None] * world
         dist.all_gather_object(numa_all, numa)
     assert np.array_equal(seal, seal_h), "device-resident and host-buffer paths disagree"
+
+    # ---- the same with the accum group computed on the device: code + data are uploaded, CircuitHal::accumulate (the
+    # circuit blob's witness program) runs between the data commit and the accum commit as in the reference's prove_segment, the accum
+    # trace (14 % of the bytes) never crosses the host link.  A different accum trace than Trace A's, so a SECONDARY number.
+    e2e_dev_accum = None
+    if not heavy and timeline is None:
+        try:
+            first_up = [threading.Event() for _ in range(inflight)]
+            run_host(inflight, h_accum="device")
+            barrier()
+            first_up = [threading.Event() for _ in range(inflight)]
+            hal.timer_start()
+            run_host(args.steps, h_accum="device")
+            ms_da = hal.timer_stop()
+            barrier()
+            t = torch.tensor([ms_da], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_dev_accum = {"value": world * args.steps / (float(t.item()) / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int((d_code.numel() + d_data.numel()) * 4),
+                             "what": "secondary: code + data groups from pinned host memory, accum group computed on the device by the circuit's witness program inside zkb_prove_staged"}
+        except Exception as e:      # noqa: BLE001  (every rank raises or none: the circuit is the same everywhere)
+            e2e_dev_accum = {"unavailable": str(e)[:200]}
 
     # ---- BASELINE metric "e2e TLS prove s": one TLS session = S continuation segments (S = 64 for a
     # 64 KB AES-128-GCM response), segment i -> rank i mod N, every segment uploaded from pinned host memory and its seal read back
@@ -522,7 +545,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": trace_bytes, "d2h_bytes_per_step": int(seal.size * 4),
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k",
                         "per_rank_ms_per_step": [round(x / args.steps, 3) for x in e2e_per_rank],
-                        "host_numa_binding_per_rank": numa_all},
+                        "host_numa_binding_per_rank": numa_all, "device_accumulate": e2e_dev_accum},
                 "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if heavy:
             line["config"]["workload"] = "SECONDARY synheavy280-segment-po2-20: the benchmark segment's shape (280 columns, 2^20 cycles, Trace A) under the SYN-HEAVY " \

@@ -169,7 +169,9 @@ zkb_err zkb_prove_segment(zkb_prover* p, int po2, const uint32_t* h_io, const vo
 /* Pipelined form for a queue of segments (the continuation segments of one session): zkb_prover_stage_traces starts the
  * host->device copy of a segment's three trace groups (pinned host memory recommended) on a separate copy stream into one of
  * two staging slots and returns at once; zkb_prove_staged proves the oldest staged segment (as zkb_prove_segment does).
- * Staging segment k+1 before proving segment k overlaps its upload with the proof.  At most two segments may be staged. */
+ * Staging segment k+1 before proving segment k overlaps its upload with the proof.  At most two segments may be staged.
+ * h_accum may be NULL when the circuit blob carries a witness program: zkb_prove_staged then runs CircuitHal::accumulate on
+ * the device between the data commit and the accum commit (prove_segment's order), and the accum group is never uploaded. */
 zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, const void* h_data, const void* h_accum);
 zkb_err zkb_prove_staged(zkb_prover* p, const uint32_t* h_io);
 /* Blocks until every upload started by zkb_prover_stage_traces on this prover has landed (lets several provers that share

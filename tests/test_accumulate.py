@@ -104,3 +104,31 @@ def test_segment_proof_with_device_side_accumulate(hal, oracle, shape, po2):
     assert np.array_equal(seal, seal_o)
     verify_segment(blob, seal, control_id(po2, op.roots()[0]))
     gp.close()
+
+
+@pytest.mark.parametrize("shape,po2", [(SMALL, 9), (MID, 11)])
+def test_staged_proof_computes_the_accum_group_on_the_device(hal, oracle, shape, po2):
+    """zkb_prover_stage_traces with a NULL accum trace: zkb_prove_staged runs the witness program between the data commit and the accum
+    commit (prove_segment's order) over a zeroed group; seal = oracle prover fed with the oracle's accumulate of the same inputs;
+    two segments through the two staging slots give the same seal; a circuit without a witness program is refused."""
+    from zktls_b200.prover import SegmentProver, verify_segment, control_id
+    from zktls_b200._lib import ZkbError
+    blob = circuit.syn_circuit(**shape).blob()
+    io, code, data = synth.trace_b_code_data(shape, po2, seed=33)
+    code_m, data_m = synth.to_mont(code), synth.to_mont(data)
+    gp = SegmentProver(hal, blob)
+    gp.stage(po2, code_m, data_m); gp.stage(po2, code_m, data_m)
+    seal1 = gp.prove_staged(io); seal2 = gp.prove_staged(io)
+    op = oracle.Prover(blob)
+    mix = op.begin(po2, io, code_m, data_m)
+    n = 1 << po2
+    accum_o = oracle.accumulate(blob, np.zeros(shape["accum_cols"] * n, np.uint32), code_m.reshape(-1), data_m.reshape(-1), mix, io, po2)
+    seal_o = op.finish(accum_o)
+    assert np.array_equal(seal1, seal_o) and np.array_equal(seal2, seal_o)
+    verify_segment(blob, seal1, control_id(po2, op.roots()[0]))
+    gp.close()
+    b = circuit.syn_circuit(**shape); b.wsteps = []
+    gq = SegmentProver(hal, b.blob())
+    with pytest.raises(ZkbError, match="no witness program"):
+        gq.stage(po2, code_m, data_m)
+    gq.close()

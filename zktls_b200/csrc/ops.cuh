@@ -32,6 +32,8 @@ void batch_evaluate_any(zkb_ctx* ctx, const uint32_t* coeffs, int po2, const uin
                         bool coeffs_bit_reversed = false);
 void poly_divide(zkb_ctx* ctx, uint32_t* d_poly, size_t n, const Fp4& z, uint32_t* d_rem);
 void prefix_products(zkb_ctx* ctx, uint32_t* d_io, size_t n);
+// CircuitHal::accumulate: the circuit blob's witness program, phase by phase (k_accum.cu)
+void accumulate(zkb_ctx* ctx, const CircuitDef& c, uint32_t* d_accum, const uint32_t* d_code, const uint32_t* d_data, const uint32_t* h_mix, const uint32_t* h_io, int po2);
 // k_eval_check.cu
 void eval_check(zkb_ctx* ctx, uint32_t* d_check, const CircuitDef& c, const uint32_t* const d_groups[3], const uint32_t* mix_g, const uint32_t* out_g,
                 const Fp4& poly_mix, int po2);

@@ -165,6 +165,7 @@ struct zkb_prover {
     cudaEvent_t consumed = nullptr;
     int po2 = -1;
     bool full = false;
+    bool device_accum = false;      // no accum trace was staged: zkb_prove_staged fills the group with the circuit's witness program
   };
   TraceSlot slots[2];
   cudaStream_t copy_stream = nullptr;
@@ -199,9 +200,10 @@ struct zkb_prover {
         ZKB_CUDA(cudaMalloc((void**)&sl.buf[g], std::max<size_t>(words, 4) * 4));
         sl.words[g] = words;
       }
-      if (words) ZKB_CUDA(cudaMemcpyAsync(sl.buf[g], h_traces[g], words * 4, cudaMemcpyHostToDevice, copy_stream));
+      if (words && h_traces[g]) ZKB_CUDA(cudaMemcpyAsync(sl.buf[g], h_traces[g], words * 4, cudaMemcpyHostToDevice, copy_stream));
       ZKB_CUDA(cudaEventRecord(sl.uploaded[g], copy_stream));
     }
+    sl.device_accum = h_traces[GROUP_ACCUM] == nullptr && circuit.group_size[GROUP_ACCUM] != 0;
     sl.po2 = po2_; sl.full = true;
     stage_idx ^= 1;
   }
@@ -211,6 +213,12 @@ struct zkb_prover {
     struct Guard { const cudaEvent_t*& r; ~Guard() { r = nullptr; } } guard{group_ready};      // also on an error path
     group_ready = sl.uploaded;
     segment_begin(sl.po2, h_io, sl.buf[GROUP_CODE], sl.buf[GROUP_DATA], true, nullptr);
+    if (sl.device_accum) {
+      // the reference's prove_segment order: commit code + data, draw `mix`, CircuitHal::accumulate, commit accum -- with the witness
+      // program of the circuit blob run on the device, so this group (14 % of SYN-280's trace bytes) never crosses the host link
+      ZKB_CUDA(cudaMemsetAsync(sl.buf[GROUP_ACCUM], 0, sl.words[GROUP_ACCUM] * 4, ctx->stream));
+      accumulate(ctx, circuit, sl.buf[GROUP_ACCUM], sl.buf[GROUP_CODE], sl.buf[GROUP_DATA], mix.data(), io.data(), sl.po2);
+    }
     segment_finish(sl.buf[GROUP_ACCUM], true);
     ZKB_CUDA(cudaEventRecord(sl.consumed, ctx->stream));
     sl.full = false;
@@ -518,7 +526,8 @@ zkb_err zkb_prover_stage_traces(zkb_prover* p, int po2, const void* h_code, cons
   use(p->ctx);
   const void* tr[3];
   tr[GROUP_ACCUM] = h_accum; tr[GROUP_CODE] = h_code; tr[GROUP_DATA] = h_data;
-  for (int g = 0; g < 3; ++g) ZKB_REQUIRE(tr[g] || p->circuit.group_size[g] == 0, "null trace");
+  for (int g = 0; g < 3; ++g) ZKB_REQUIRE(tr[g] || p->circuit.group_size[g] == 0 || (g == GROUP_ACCUM && !p->circuit.wsteps.empty()),
+                                          g == GROUP_ACCUM ? "null accum trace and the circuit blob carries no witness program to compute it" : "null trace");
   p->stage_traces(po2, tr);
   ZKB_API_END
 }

@@ -55,12 +55,14 @@ class SegmentProver:
         check(lib().zkb_prove_segment(self.h, C.c_int(po2), _hp(io), self._ptr(c, cd), self._ptr(d, dd), self._ptr(a, ad), C.c_int(int(cd))))
         return self.seal()
 
-    def stage(self, po2, code, data, accum):
+    def stage(self, po2, code, data, accum=None):
         """Starts the asynchronous upload of one segment's host traces (numpy arrays, ideally over pinned memory) into a
-        staging slot; returns immediately.  The arrays must stay alive and unmodified until the matching prove_staged()."""
-        arrs = [np.ascontiguousarray(t, dtype=np.uint32) for t in (code, data, accum)]
+        staging slot; returns immediately.  The arrays must stay alive and unmodified until the matching prove_staged().
+        accum=None: the accum group is computed on the device by the circuit's witness program (CircuitHal::accumulate) inside
+        prove_staged and never uploaded."""
+        arrs = [None if t is None else np.ascontiguousarray(t, dtype=np.uint32) for t in (code, data, accum)]
         self._staged = getattr(self, "_staged", []) + [arrs]
-        check(lib().zkb_prover_stage_traces(self.h, C.c_int(po2), *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
+        check(lib().zkb_prover_stage_traces(self.h, C.c_int(po2), *[C.c_void_p(None) if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]))
 
     def stage_wait(self):
         check(lib().zkb_prover_stage_wait(self.h))
