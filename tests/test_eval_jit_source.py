@@ -64,3 +64,31 @@ def test_staged_and_register_forms_evaluate_the_same_program():
     arith = lambda s: [l.strip() for l in s.splitlines() if any(k in l for k in ("wacc(", "= mul(", "= sub(", "= add(", "scale4(", "fin("))
                        and "__device__" not in l]
     assert arith(a) == arith(b) and len(arith(a)) > 10
+
+
+def test_the_jit_compiler_does_not_depend_on_import_order(tmp_path):
+    """A process that imported torch first has torch's bundled libnvrtc mapped under the SONAME libnvrtc.so.12; the loader must still pick
+    the same (newest) NVRTC as a process that did not -- the compact eval_check form ran 8 % slower when it silently got the older one
+    (profiles/r2_y_nvrtc_version.txt), and the on-disk cubin cache is keyed by the NVRTC version, so the shipped cubins were missed too."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    body = ("import ctypes as C, numpy as np\n"
+            "from zktls_b200 import circuit\n"
+            "from zktls_b200._lib import check, lib\n"
+            "b = circuit.syn_circuit(accum_cols=4, code_cols=3, data_cols=6, mix_size=5, out_size=4).blob()\n"
+            "check(lib().zkb_eval_check_precompile(b.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(b.size)))\n")
+    seen = {}
+    for tag, prefix in (("plain", ""), ("torch first", "import torch\n")):
+        env = dict(os.environ, ZKB_EC_VERBOSE="1", ZKB_CACHE_DIR=str(tmp_path / tag.replace(" ", "_")), PYTHONPATH=root)
+        env.pop("ZKB_NVRTC_LIB", None)
+        os.makedirs(env["ZKB_CACHE_DIR"], mode=0o700)
+        r = subprocess.run([sys.executable, "-c", prefix + body], env=env, capture_output=True, text=True, timeout=600)
+        if "not loadable" in r.stderr:
+            pytest.skip("no NVRTC in this environment")
+        assert r.returncode == 0, r.stderr[-2000:]
+        m = re.search(r"zkb200: NVRTC (\d+)\.(\d+) from (\S+)", r.stderr)
+        assert m, r.stderr[-2000:]
+        seen[tag] = (int(m.group(1)), int(m.group(2)), m.group(3))
+    assert seen["plain"] == seen["torch first"], seen
