@@ -546,7 +546,10 @@ def main():
                         "pipeline": "zkb_prover_stage_traces + zkb_prove_staged: pinned host traces, upload of segment k+1 overlaps the proof of segment k",
                         "per_rank_ms_per_step": [round(x / args.steps, 3) for x in e2e_per_rank],
                         "host_numa_binding_per_rank": numa_all, "device_accumulate": e2e_dev_accum},
-                "gpu_launches": int(launches), "tls_session": session, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
+                "gpu_launches": int(launches), "tls_session": session,
+                "config5_estimate": {"what": "BASELINE configs[4] (64 sessions -> succinct receipts), SEGMENT STAGE ONLY, extrapolated from the measured end-to-end rate "
+                                             "(SURVEY.md 8d: 64 x 40 SYN-280 segments; lift / join need the recursion circuit, which is not built)",
+                                     "segments": 2560, "estimated_seconds": 2560.0 / e2e_value, "sessions_per_hour": e2e_value * 3600.0 / 40.0}, "roofline": roof, "cpu_baseline": cpu, "wall_s": wall, "seal_words": int(seal.size)}
         if heavy:
             line["config"]["workload"] = "SECONDARY synheavy280-segment-po2-20: the benchmark segment's shape (280 columns, 2^20 cycles, Trace A) under the SYN-HEAVY " \
                                          "constraint system (rv32im-shaped: 22 k constraints / 117 k PolyExtSteps, AndCond depth 4, taps back 0..4, 5 combos) -- eval_check-weighted companion of the headline"

@@ -102,6 +102,11 @@ zkb_err zkb_mix_poly_coeffs(zkb_ctx* ctx, void* d_out, const uint32_t* h_mix_sta
 /* Device version of the host step in Prover::finalize (core/poly.rs poly_divide): synthetic division of the
  * Fp4 polynomial d_poly[0..n) by (x - z) in place; writes the remainder (4 words) to d_rem. */
 zkb_err zkb_poly_divide(zkb_ctx* ctx, void* d_poly, size_t n, const uint32_t* h_z, void* d_rem);
+/* The whole division step of Prover::finalize (SURVEY.md 8b `zkb_combos_divide`): d_combos holds n_combos Fp4 polynomials of n
+ * coefficients each; division k < n_div divides polynomial h_combo[k] by (x - h_points[4k..4k+4)) in place, in the order given;
+ * the n_div remainders (4 words each) are written to h_rem after one synchronisation. */
+zkb_err zkb_combos_divide(zkb_ctx* ctx, void* d_combos, size_t n, size_t n_combos, const uint32_t* h_combo, const uint32_t* h_points,
+                          size_t n_div, uint32_t* h_rem);
 /* Hal::eltwise_sum_extelem(out, in): out[j*count+idx] = (sum_k in[k*count+idx])[j]. */
 zkb_err zkb_eltwise_sum_extelem(zkb_ctx* ctx, void* d_out, const void* d_in, size_t count, size_t to_add);
 /* Hal::fri_fold(out, in, mix): out_count = out.len/4; in.len = 64*out_count. */

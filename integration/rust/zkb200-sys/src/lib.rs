@@ -42,6 +42,7 @@ extern "C" {
     pub fn zkb_batch_evaluate_any(ctx: *mut ZkbCtx, d_coeffs: *const c_void, poly_count: usize, po2: c_int, d_which: *const c_void, d_xs: *const c_void, d_out: *mut c_void, n_eval: usize) -> ZkbErr;
     pub fn zkb_mix_poly_coeffs(ctx: *mut ZkbCtx, d_out: *mut c_void, h_mix_start: *const u32, h_mix: *const u32, d_in: *const c_void, d_combos: *const c_void, input_size: usize, count: usize) -> ZkbErr;
     pub fn zkb_poly_divide(ctx: *mut ZkbCtx, d_poly: *mut c_void, n: usize, h_z: *const u32, d_rem: *mut c_void) -> ZkbErr;
+    pub fn zkb_combos_divide(ctx: *mut ZkbCtx, d_combos: *mut c_void, n: usize, n_combos: usize, h_combo: *const u32, h_points: *const u32, n_div: usize, h_rem: *mut u32) -> ZkbErr;
     pub fn zkb_eltwise_sum_extelem(ctx: *mut ZkbCtx, d_out: *mut c_void, d_in: *const c_void, count: usize, to_add: usize) -> ZkbErr;
     pub fn zkb_fri_fold(ctx: *mut ZkbCtx, d_out: *mut c_void, d_in: *const c_void, h_mix: *const u32, out_count: usize) -> ZkbErr;
     pub fn zkb_eltwise_add_elem(ctx: *mut ZkbCtx, d_out: *mut c_void, d_a: *const c_void, d_b: *const c_void, n: usize) -> ZkbErr;

@@ -152,6 +152,22 @@ def test_poly_divide(hal, oracle, n):
     assert np.array_equal(b.to_numpy(), q) and np.array_equal(rem, r)
 
 
+@pytest.mark.parametrize("n", [1, 700, 1 << 13])
+def test_combos_divide(hal, oracle, n):
+    """the division step of Prover::finalize in one call: a combo is divided once per tap offset it holds, in order"""
+    combos = rnd(950 + n, 3 * 4 * n).reshape(3, 4 * n)
+    order, pts = [0, 2, 2, 1, 2], rnd(951 + n, 5 * 4).reshape(5, 4)
+    b = hal.copy_from_extelem(combos.reshape(-1))
+    rems = hal.combos_divide(b, n, order, pts)
+    want = [c.copy() for c in combos]
+    for k, c in enumerate(order):
+        want[c], r = oracle.poly_divide(want[c], pts[k])
+        assert np.array_equal(rems[k], r)
+    assert np.array_equal(b.to_numpy(), np.concatenate(want))
+    with pytest.raises(Exception, match="out of range"):
+        hal.combos_divide(b, n, [3], pts[:1])
+
+
 @pytest.mark.parametrize("count,to_add", [(1, 1), (100, 3), (1 << 12, 4)])
 def test_eltwise_sum_extelem(hal, oracle, count, to_add):
     inp = rnd(1000 + count, 4 * count * to_add)

@@ -23,7 +23,7 @@ SYMBOLS = [
     "zkb_batch_interpolate_ntt", "zkb_zk_shift", "zkb_batch_interpolate_ntt_zk_shift", "zkb_batch_expand", "zkb_batch_evaluate_ntt",
     "zkb_batch_expand_into_evaluate_ntt", "zkb_batch_bit_reverse",
     "zkb_poseidon2_hash_rows", "zkb_poseidon2_hash_fold", "zkb_poseidon2_merkle_build",
-    "zkb_batch_evaluate_any", "zkb_mix_poly_coeffs", "zkb_poly_divide", "zkb_eltwise_sum_extelem", "zkb_fri_fold",
+    "zkb_batch_evaluate_any", "zkb_mix_poly_coeffs", "zkb_poly_divide", "zkb_combos_divide", "zkb_eltwise_sum_extelem", "zkb_fri_fold",
     "zkb_eltwise_add_elem", "zkb_eltwise_copy_elem", "zkb_eltwise_zeroize_elem", "zkb_gather_sample", "zkb_gather_rows", "zkb_prefix_products", "zkb_scatter",
     "zkb_eval_check", "zkb_eval_check_source", "zkb_eval_check_precompile", "zkb_accumulate",
     "zkb_prover_new", "zkb_prover_free", "zkb_prover_segment_begin", "zkb_prover_segment_finish", "zkb_prover_seal_words",

@@ -706,5 +706,22 @@ zkb_err zkb_poly_divide(zkb_ctx* ctx, void* d_poly, size_t n, const uint32_t* h_
   poly_divide(ctx, (uint32_t*)d_poly, n, Fp4::load(h_z), (uint32_t*)d_rem);
   ZKB_API_END
 }
+// SURVEY.md 8(b) `zkb_combos_divide`: the whole division step of Prover::finalize in one call -- division k divides combo polynomial
+// h_combo[k] (n Fp4 coefficients at d_combos + 4 n h_combo[k] words) by (x - h_points[k]) in place, in the order given (a combo is divided
+// once per tap offset it holds); the n_div remainders come back together (one synchronisation instead of one per quotient).
+zkb_err zkb_combos_divide(zkb_ctx* ctx, void* d_combos, size_t n, size_t n_combos, const uint32_t* h_combo, const uint32_t* h_points, size_t n_div, uint32_t* h_rem) {
+  ZKB_API_BEGIN use(ctx);
+  if (!n_div) return nullptr;
+  ZKB_REQUIRE(d_combos && h_combo && h_points && h_rem && aligned16(d_combos), "null or misaligned buffer");
+  ZKB_REQUIRE(n >= 1, "combos_divide: empty polynomials");
+  for (size_t k = 0; k < n_div; ++k) ZKB_REQUIRE(h_combo[k] < n_combos, "combos_divide: combo index out of range");
+  uint32_t* d_rem = nullptr;
+  pool_alloc(ctx, &d_rem, n_div * 16);
+  for (size_t k = 0; k < n_div; ++k) poly_divide(ctx, (uint32_t*)d_combos + (size_t)h_combo[k] * n * 4, n, Fp4::load(h_points + 4 * k), d_rem + 4 * k);
+  ZKB_CUDA(cudaMemcpyAsync(h_rem, d_rem, n_div * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  ZKB_CUDA(cudaStreamSynchronize(ctx->stream));
+  pool_free(ctx, d_rem);
+  ZKB_API_END
+}
 
 }  // extern "C"

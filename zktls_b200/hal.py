@@ -188,6 +188,14 @@ class B200Hal:
         check(lib().zkb_poly_divide(self.ctx, C.c_void_p(poly.ptr), _sz(poly.size), _hp(zz), C.c_void_p(rem.ptr)))
         return rem.to_numpy()
 
+    def combos_divide(self, combos, n, combo, points):
+        """Prover::finalize's division step in one call: polynomial combo[k] of `combos` (n Fp4 coefficients each) is divided in place
+        by (x - points[k]); returns the remainders, one row of 4 words per division."""
+        combo = np.ascontiguousarray(combo, np.uint32); pts = np.ascontiguousarray(points, np.uint32).reshape(-1, 4)
+        rem = np.zeros((combo.size, 4), np.uint32)
+        check(lib().zkb_combos_divide(self.ctx, C.c_void_p(combos.ptr), _sz(n), _sz(combos.size // n), _hp(combo), _hp(pts), _sz(combo.size), _hp(rem)))
+        return rem
+
     def eltwise_sum_extelem(self, out, inp):
         count = out.size // 4
         check(lib().zkb_eltwise_sum_extelem(self.ctx, C.c_void_p(out.ptr), C.c_void_p(inp.ptr), _sz(count), _sz(inp.size // count)))
