@@ -622,6 +622,7 @@ zkb_err zkb_gather_rows(zkb_ctx* ctx, void* d_dst, const void* d_src, size_t src
   if (!n_idx || !size) return nullptr;
   ZKB_REQUIRE(d_dst && d_src && h_idx, "null buffer");
   ZKB_REQUIRE(n_idx <= 65535, "gather_rows: more than 65535 rows in one call");
+  ZKB_REQUIRE(stride == 0 || (size - 1) <= (src_len ? src_len - 1 : 0) / stride, "gather_rows: a row reaches outside the source buffer");      // (no overflow in the product below)
   for (size_t q = 0; q < n_idx; ++q) ZKB_REQUIRE((size_t)h_idx[q] + (size - 1) * stride < src_len, "gather_rows: a row reaches outside the source buffer");
   uint32_t* d_idx = nullptr;
   pool_alloc(ctx, &d_idx, n_idx * 4);
