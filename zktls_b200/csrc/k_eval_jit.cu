@@ -854,7 +854,7 @@ static bool generate_compact_ppt(const CircuitDef& c, GenInfo& gi, std::string& 
   // twice as many independent chains per warp.  The block keeps 512 threads as 8 groups of 64, with correspondingly smaller units.
   // Measured on SYN-HEAVY (profiles/r2_v_ec_ppt_sweep.txt): 135.4 ms with one point per thread (main loop of 8 terms), 123.6 ms with two
   // (pairs of terms); ZKB_EC_PPT=1 restores the former.
-  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", ppt == 2 ? 8 : 4, 1, 8);
+  const uint32_t groups = env_u32("ZKB_EC_FLAT_GROUPS", ppt == 2 ? 8 : 4, 1, 15);      // (named barriers 1..15)
   const uint32_t unit_terms = env_u32("ZKB_EC_UNIT", ppt == 2 ? 96 : 256, 8, 512);
   const uint32_t unit_vecs = env_u32("ZKB_EC_UNIT_VECS", ppt == 2 ? 240 : 640, 64, 4096);          // operand-table granules (16 B) a unit may use
   uint32_t points = env_u32("ZKB_EC_FLAT_POINTS", 128, 32, 512);
